@@ -1,0 +1,305 @@
+"""ctypes binding of libodo_b200.so (include/odo_b200.h) for tests and bench.py.
+
+This is plumbing: every function here forwards to the C-ABI, which is the only way to reach the
+CUDA kernels.  There is NO CPU fallback: if the library is missing or no CUDA device is present the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libodo_b200.so")
+MAX_LEVELS = 8
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("fx", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class LMParams(C.Structure):
+    _fields_ = [("lam", C.c_float), ("precision", C.c_float), ("max_iters", C.c_int * MAX_LEVELS),
+                ("robust", C.c_int), ("huber_delta", C.c_float), ("K", Intrinsics)]
+
+
+class LMStats(C.Structure):
+    _fields_ = [("iters", C.c_int * MAX_LEVELS), ("n_res", C.c_int * MAX_LEVELS),
+                ("err", C.c_float * MAX_LEVELS), ("status", C.c_int)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("grad_th", C.c_float), ("ssd_th", C.c_float), ("photo_th", C.c_float),
+                ("min_depth", C.c_float), ("max_depth", C.c_float), ("lam", C.c_float),
+                ("huber_delta", C.c_float), ("precision", C.c_float), ("max_iters", C.c_int),
+                ("boundary", C.c_int), ("max_residuals", C.c_int), ("baseline", C.c_float),
+                ("fx", C.c_float)]
+
+
+class DepthStats(C.Structure):
+    _fields_ = [("n_selected", C.c_int), ("n_matched", C.c_int), ("n_valid", C.c_int),
+                ("iters", C.c_int), ("cost", C.c_float), ("status", C.c_int)]
+
+
+EXPORTS = [
+    "odo_version", "odo_ctx_create", "odo_ctx_destroy", "odo_ctx_sync", "odo_last_error",
+    "odo_ctx_launch_count", "odo_default_intrinsics", "odo_default_lm_params",
+    "odo_default_depth_params", "odo_image_pyramid_build", "odo_depth_pyramid_build",
+    "odo_pyr_levels", "odo_pyr_level_size", "odo_pyr_download", "odo_pyr_release",
+    "odo_compute_depth", "odo_select_pixels", "odo_disparity_search", "odo_depth_optimize",
+    "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
+    "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libodo_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python odometry_b200/build.py` "
+                               "(there is no CPU fallback for the product path)")
+        L = C.CDLL(LIB_PATH)
+        L.odo_version.restype = C.c_char_p
+        L.odo_last_error.restype = C.c_char_p
+        L.odo_last_error.argtypes = [C.c_void_p]
+        L.odo_ctx_launch_count.restype = C.c_int64
+        L.odo_ctx_launch_count.argtypes = [C.c_void_p]
+        L.odo_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.odo_ctx_destroy.argtypes = [C.c_void_p]
+        L.odo_ctx_sync.argtypes = [C.c_void_p]
+        L.odo_pyr_release.argtypes = [C.c_void_p, C.c_void_p]
+        L.odo_pyr_levels.argtypes = [C.c_void_p]
+        L.odo_tracker_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=C.c_float):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _colmajor(T):
+    return _f32(np.asarray(T, dtype=np.float32).T).ravel()
+
+
+def default_lm_params(**kw) -> LMParams:
+    p = LMParams()
+    lib().odo_default_lm_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "max_iters":
+            for i in range(MAX_LEVELS):
+                p.max_iters[i] = v[i] if i < len(v) else 0
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def default_depth_params(**kw) -> DepthParams:
+    p = DepthParams()
+    lib().odo_default_depth_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class OdoError(RuntimeError):
+    pass
+
+
+class Pyramid:
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def levels(self):
+        return lib().odo_pyr_levels(self.h)
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        if lib().odo_pyr_level_size(self.h, l, C.byref(w), C.byref(h)) != 0:
+            raise OdoError("bad level")
+        return w.value, h.value
+
+    def download(self, l):
+        w, h = self.level_size(l)
+        out = np.empty((h, w), np.float32)
+        if lib().odo_pyr_download(self.ctx.h, self.h, l, _p(out)) != 0:
+            raise OdoError(self.ctx.last_error())
+        return out
+
+    def release(self):
+        if self.h:
+            lib().odo_pyr_release(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        rc = lib().odo_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0 or not h:
+            raise OdoError("odo_ctx_create failed (no CUDA device?) -- there is no CPU fallback")
+        self.h = h
+
+    def last_error(self):
+        return lib().odo_last_error(self.h).decode()
+
+    def sync(self):
+        if lib().odo_ctx_sync(self.h) != 0:
+            raise OdoError(self.last_error())
+
+    def launch_count(self):
+        return int(lib().odo_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib().odo_ctx_destroy(self.h)
+            self.h = None
+
+    # ---- pyramids
+    def image_pyramid(self, img, levels=4, smooth=True) -> Pyramid:
+        img = _f32(img)
+        hgt, wid = img.shape
+        out = C.c_void_p()
+        if lib().odo_image_pyramid_build(self.h, _p(img), wid, hgt, levels, int(bool(smooth)), C.byref(out)) != 0:
+            raise OdoError(self.last_error())
+        return Pyramid(self, out)
+
+    def depth_pyramid(self, dep, levels=4, smooth=False) -> Pyramid:
+        dep = _f32(dep)
+        hgt, wid = dep.shape
+        out = C.c_void_p()
+        if lib().odo_depth_pyramid_build(self.h, _p(dep), wid, hgt, levels, int(bool(smooth)), C.byref(out)) != 0:
+            raise OdoError(self.last_error())
+        return Pyramid(self, out)
+
+    # ---- LM
+    def lm_solve(self, pyr1: Pyramid, dep1: Pyramid, pyr2: Pyramid, params: LMParams, T_init=None):
+        T0 = _colmajor(np.eye(4, dtype=np.float32) if T_init is None else T_init)
+        Tout = np.empty(16, np.float32)
+        st = LMStats()
+        rc = lib().odo_lm_solve(self.h, pyr1.h, dep1.h, pyr2.h, C.byref(params), _p(T0), _p(Tout), C.byref(st))
+        return rc, Tout.reshape(4, 4).T.copy(), st
+
+    def lm_linearize(self, pyr1, dep1, pyr2, level, T, robust=1, huber_delta=28.0):
+        Tc = _colmajor(T)
+        H = np.zeros(21, np.float64)
+        g = np.zeros(6, np.float64)
+        E, N, sigma = C.c_double(), C.c_int(), C.c_float()
+        rc = lib().odo_lm_linearize(self.h, pyr1.h, dep1.h, pyr2.h, level, _p(Tc), robust, C.c_float(huber_delta),
+                                    None, _p(H, C.c_double), _p(g, C.c_double), C.byref(E), C.byref(N), C.byref(sigma))
+        return dict(rc=rc, H=H, g=g, E=E.value, N=N.value, sigma=sigma.value)
+
+    # ---- depth
+    def select_pixels(self, L, R, p: DepthParams):
+        L, R = _f32(L), _f32(R)
+        h, w = L.shape
+        bl, br = np.empty_like(L), np.empty_like(R)
+        val = np.zeros((h, w), np.uint8)
+        rc = lib().odo_select_pixels(self.h, _p(L), _p(R), w, h, C.byref(p), _p(bl), _p(br), _p(val, C.c_uint8))
+        return rc, bl, br, val
+
+    def disparity_search(self, bl, br, val, p: DepthParams):
+        bl, br = _f32(bl), _f32(br)
+        h, w = bl.shape
+        val = np.ascontiguousarray(val, np.uint8)
+        disp = np.zeros((h, w), np.float32)
+        dep = np.zeros((h, w), np.float32)
+        match = np.zeros((h, w), np.int32)
+        ssd = np.zeros((h, w), np.float32)
+        rc = lib().odo_disparity_search(self.h, _p(bl), _p(br), w, h, C.byref(p), _p(val, C.c_uint8), _p(disp),
+                                        _p(dep), _p(match, C.c_int32), _p(ssd))
+        return rc, disp, dep, match, ssd
+
+    def depth_optimize(self, L, R, dep, val, p: DepthParams):
+        L, R = _f32(L), _f32(R)
+        h, w = L.shape
+        dep = _f32(dep).copy()
+        val = np.ascontiguousarray(val, np.uint8).copy()
+        st = DepthStats()
+        rc = lib().odo_depth_optimize(self.h, _p(L), _p(R), w, h, C.byref(p), _p(dep), _p(val, C.c_uint8), C.byref(st))
+        return rc, dep, val, st
+
+    def compute_depth(self, L, R, p: DepthParams):
+        L, R = _f32(L), _f32(R)
+        h, w = L.shape
+        val = np.zeros((h, w), np.uint8)
+        disp = np.zeros((h, w), np.float32)
+        dep = np.zeros((h, w), np.float32)
+        st = DepthStats()
+        rc = lib().odo_compute_depth(self.h, _p(L), _p(R), w, h, C.byref(p), _p(val, C.c_uint8), _p(disp), _p(dep),
+                                     C.byref(st))
+        return rc, val, disp, dep, st
+
+
+class Tracker:
+    """Batched tracking loop (odo_tracker_*): n_seq sequences, one frame per sequence per step."""
+
+    def __init__(self, ctx: Context, w, h, levels=4, n_seq=1, lm: LMParams | None = None,
+                 dp: DepthParams | None = None):
+        self.ctx, self.w, self.hgt, self.n = ctx, w, h, n_seq
+        self._lm = lm or default_lm_params()
+        self._dp = dp or default_depth_params()
+        t = C.c_void_p()
+        rc = lib().odo_tracker_create(ctx.h, w, h, levels, n_seq, C.byref(self._lm), C.byref(self._dp), C.byref(t))
+        if rc != 0:
+            raise OdoError(ctx.last_error())
+        self.h = t
+        self.pose_abs = np.zeros((n_seq, 16), np.float32)
+        self.pose_kf = np.zeros((n_seq, 16), np.float32)
+        self.is_kf = np.zeros(n_seq, np.int32)
+        self.status = np.zeros(n_seq, np.int32)
+
+    def _outs(self):
+        return (_p(self.pose_abs), _p(self.pose_kf), _p(self.is_kf, C.c_int), _p(self.status, C.c_int))
+
+    def _result(self, rc):
+        pa = self.pose_abs.reshape(self.n, 4, 4).transpose(0, 2, 1).copy()
+        pk = self.pose_kf.reshape(self.n, 4, 4).transpose(0, 2, 1).copy()
+        return rc, pa, pk, self.is_kf.copy(), self.status.copy()
+
+    def step_ptrs(self, left_ptrs, right_ptrs, u8=False):
+        """left_ptrs/right_ptrs: sequences of n_seq raw host addresses (e.g. pinned torch tensors)."""
+        arr_t = C.c_void_p * self.n
+        la, ra = arr_t(*left_ptrs), arr_t(*right_ptrs)
+        fn = lib().odo_tracker_step_u8 if u8 else lib().odo_tracker_step
+        rc = fn(self.h, la, ra, *self._outs())
+        return self._result(rc)
+
+    def step(self, lefts, rights):
+        """lefts/rights: lists of n_seq numpy images (float32, or uint8 for the fused-convert path)."""
+        u8 = lefts[0].dtype == np.uint8
+        dt = np.uint8 if u8 else np.float32
+        ls = [np.ascontiguousarray(a, dtype=dt) for a in lefts]
+        rs = [np.ascontiguousarray(a, dtype=dt) for a in rights]
+        return self.step_ptrs([a.ctypes.data for a in ls], [a.ctypes.data for a in rs], u8=u8)
+
+    def step_dev(self, left_dev_ptr, right_dev_ptr):
+        rc = lib().odo_tracker_step_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr), *self._outs())
+        return self._result(rc)
+
+    def close(self):
+        if self.h:
+            lib().odo_tracker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,148 @@
+// common.cuh -- internal declarations shared by the .cu files of libodo_b200.so.
+// Not part of the public interface (that is include/odo_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/odo_b200.h"
+
+// ---- host-side helpers ---------------------------------------------------------------------------
+struct odo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string err;
+  // scratch cache for the single-call entry points (grown on demand, freed with the context)
+  void* scratch[16] = {nullptr};
+  size_t scratch_bytes[16] = {0};
+};
+
+#define ODO_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+      return -1;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+// level geometry of a packed pyramid (integer-halved sizes, src/image_processing_global.cpp:35-49)
+struct PyrGeom {
+  int levels;
+  int w[ODO_MAX_LEVELS];
+  int h[ODO_MAX_LEVELS];
+  int64_t off[ODO_MAX_LEVELS];  // offset of level l in floats
+  int64_t total;                // floats per pyramid
+};
+
+inline PyrGeom make_geom(int w, int h, int levels) {
+  PyrGeom g;
+  g.levels = levels;
+  int64_t off = 0;
+  for (int l = 0; l < ODO_MAX_LEVELS; l++) {
+    g.w[l] = w;
+    g.h[l] = h;
+    g.off[l] = off;
+    if (l < levels) off += (int64_t)w * h;
+    w /= 2;
+    h /= 2;
+  }
+  g.total = off;
+  return g;
+}
+
+struct odo_pyr {
+  PyrGeom g;
+  float* d = nullptr;  // device, packed levels
+  int kind = 0;        // 0 image, 1 inverse depth
+};
+
+// ---- pyramid.cu ----------------------------------------------------------------------------------
+// All launchers are batched: element b of the batch lives at base + b * stride (in elements).
+void launch_u8_to_f32(odo_ctx* c, const uint8_t* src, float* dst, int64_t n);
+void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch);
+void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
+                    int dw, int dh, int batch);
+void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
+                          const PyrGeom& g, int smooth, int batch);
+void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,
+                          const PyrGeom& g, int smooth, int batch);
+
+// ---- lm.cu ---------------------------------------------------------------------------------------
+// Per keyframe, per level: compacted list of the residual candidates (interior pixels with a valid
+// inverse depth) with everything that does not depend on the pose precomputed.
+struct LmLists {
+  float4* pA;          // X, Y, Z, I1
+  float4* pB;          // jw: a, c, d, e0
+  float4* pC;          // jw: g, h, e1, k
+  int64_t seq_stride;  // float4 elements per sequence
+  int64_t lvl_off[ODO_MAX_LEVELS];  // offset of level l inside a sequence's block
+  int* counts;         // [batch][ODO_MAX_LEVELS]
+  int* row_cnt;        // [batch][rows_total]   scratch of the compaction
+  int* row_off;        // [batch][rows_total]
+  int rows_total;
+  int row_base[ODO_MAX_LEVELS];
+};
+size_t lm_lists_bytes(const PyrGeom& g, int batch, LmLists* layout);  // fills offsets, returns bytes needed
+void lm_lists_bind(LmLists* L, void* mem, const PyrGeom& g, int batch);
+void launch_lm_prepare(odo_ctx* c, const float* img_pyr, int64_t istride, const float* dep_pyr, int64_t dstride,
+                       const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active);
+
+struct LmLevelOut {      // sums of the last evaluation at a level (test hook / stats)
+  double H[21];
+  double g[6];
+  double E;
+  float sigma;
+  int N;
+};
+struct LmResult {        // per sequence, written by the solve kernel
+  float T[16];           // column-major result (failure value on status -1)
+  int status;
+  int iters[ODO_MAX_LEVELS];
+  int n_res[ODO_MAX_LEVELS];
+  float err[ODO_MAX_LEVELS];
+  LmLevelOut last[ODO_MAX_LEVELS];
+};
+struct LmWork {          // device scratch of the solve kernel
+  double* partials;      // [batch][2][G][32]
+  unsigned* barrier;     // [batch]
+  float4* resid;         // [batch][cap] r, gx, gy, valid (t-dist two-phase)
+  int64_t resid_stride;
+  int* abort_flag;
+};
+// G = CTAs per sequence (1 .. sm_count).  only_level >= 0: evaluate that level once at exactly T_init
+// (test hook for odo_lm_linearize).
+int launch_lm_solve(odo_ctx* c, const LmLists& L, const float* img2_pyr, int64_t i2stride, const PyrGeom& g,
+                    const odo_lm_params& p, const float* T_init_dev /*[batch][16]*/, LmResult* out_dev,
+                    LmWork wk, int batch, int G, int only_level);
+size_t lm_work_bytes(const PyrGeom& g, int batch, int G);
+void lm_work_bind(LmWork* w, void* mem, const PyrGeom& g, int batch, int G);
+
+// ---- depth.cu ------------------------------------------------------------------------------------
+struct DepthWork {
+  float* blurL;        // [batch][w*h]
+  float* blurR;
+  uint8_t* val;        // [batch][w*h]
+  float* disp;
+  float* dep;
+  int* match_x;        // optional (test hook), [batch][w*h]
+  float* min_ssd;      // optional
+  int* sel_xy;         // [batch][cap] packed (y << 16 | x), -1 = hole; block-major selection order
+  int* sel_count;      // [batch][512] per 16x32 block
+  odo_depth_stats* stats;  // [batch]
+  float* ref_state;    // refinement scratch [batch][cap][4]
+  int cap;
+};
+size_t depth_work_bytes(int w, int h, int batch, bool debug);
+int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)
+void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debug);
+void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+                   const odo_depth_params& p, DepthWork d, int batch);
+void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch);
+void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+                         const odo_depth_params& p, DepthWork d, int batch);

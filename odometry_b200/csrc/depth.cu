@@ -1,0 +1,481 @@
+// depth.cu -- semi-dense stereo depth on the device (sm_100a).
+//
+// Replaces DepthEstimator::DisparityDepthEstimate (src/depth_estimate.cpp:244-401),
+// ComputeSsdPattern8Sse (:435-453) and DepthOptimization / ComputeResidualJacobian (:80-242).
+//
+//   k_select     one CTA per block of the reference's 16x32 grid: central-difference gradient
+//                magnitude of the blurred left image, exact median by a 4-pass radix select on the
+//                float bit patterns (std::nth_element at n/2), threshold median + grad_th, first
+//                <= 80 pixels in raster order by an ordered ballot/popc scan.
+//   k_disparity  one CTA per (image row, 64-pixel segment) that holds selected pixels: the five right
+//                rows y-2..y+2 are staged in shared memory once, then one warp per selected pixel
+//                walks the candidates right_x = boundary .. x-1 (lane-strided, conflict-free), with the
+//                8-tap SSD in the exact association of the reference's AVX hadd tree, a per-lane
+//                first-minimum and a warp-shuffle argmin with the smaller-column tie rule.
+//   k_refine     persistent per-sequence group of CTAs: the per-pixel 1-D LM on inverse depth with the
+//                GLOBAL accept/reject of the reference (error summed over all pixels in fp64 through the
+//                deterministic group all-reduce), no host round trip per iteration.
+// Built with -fmad=false; the SSD uses explicit round-to-nearest sub/mul/add.
+#include "common.cuh"
+#include "group_sync.cuh"
+
+namespace {
+
+constexpr int kSelMax = 80;       // "if (valid_count >= 80) break", src/depth_estimate.cpp:333-339
+constexpr int kGridBlocks = 512;  // 16 x 32, :302
+
+// ---- selection --------------------------------------------------------------------------------------
+__device__ __forceinline__ float grad_mag(const float* __restrict__ bl, int W, int y, int x) {
+  // :315-317 on the blurred left image
+  const float gx = __fmul_rn(0.5f, __fsub_rn(__ldg(bl + (int64_t)y * W + x + 1), __ldg(bl + (int64_t)y * W + x - 1)));
+  const float gy = __fmul_rn(0.5f, __fsub_rn(__ldg(bl + (int64_t)(y + 1) * W + x), __ldg(bl + (int64_t)(y - 1) * W + x)));
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+}
+
+constexpr int kSelThreads = 256;
+constexpr int kMagCache = 2048;
+
+__global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_params p, DepthWork d) {
+  const int b = blockIdx.y, block_id = blockIdx.x;
+  const int64_t npx = (int64_t)W * H;
+  const float* bl = d.blurL + b * npx;
+  uint8_t* val = d.val + b * npx;
+  const int bw = (W - p.boundary * 2) / 32, bh = (H - p.boundary * 2) / 16;
+  const int start_y = p.boundary + (block_id / 32) * bh;
+  const int start_x = p.boundary + (block_id % 32) * bw;
+  const int n = bw * bh;
+  __shared__ float s_mag[kMagCache];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_prefix, s_k;
+  __shared__ int s_w[kSelThreads / 32];
+  const bool cached = n <= kMagCache;
+  if (cached)
+    for (int i = threadIdx.x; i < n; i += kSelThreads) s_mag[i] = grad_mag(bl, W, start_y + i / bw, start_x + i % bw);
+  if (threadIdx.x == 0) {
+    s_prefix = 0u;
+    s_k = (unsigned)(n / 2);  // block_grad.begin() + block_grad.size()/2, :324
+  }
+  __syncthreads();
+  // exact k-th smallest: magnitudes are >= +0, so the uint32 bit pattern orders like the float
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int i = threadIdx.x; i < 256; i += kSelThreads) s_hist[i] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned hi_mask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
+    for (int i = threadIdx.x; i < n; i += kSelThreads) {
+      const float m = cached ? s_mag[i] : grad_mag(bl, W, start_y + i / bw, start_x + i % bw);
+      const unsigned u = __float_as_uint(m);
+      if ((u & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(u >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned k = s_k, cum = 0u;
+      int bin = 0;
+      for (; bin < 256; bin++) {
+        if (cum + s_hist[bin] > k) break;
+        cum += s_hist[bin];
+      }
+      if (bin > 255) bin = 255;
+      s_k = k - cum;
+      s_prefix = prefix | ((unsigned)bin << (8 * pass));
+    }
+    __syncthreads();
+  }
+  const float block_th = __fadd_rn(__uint_as_float(s_prefix), p.grad_th);  // :325
+  // first <= 80 pixels with mag > th in raster order, :327-341
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int run = 0;
+  for (int i0 = 0; i0 < n && run < kSelMax; i0 += kSelThreads) {
+    const int i = i0 + threadIdx.x;
+    bool f = false;
+    int y = 0, x = 0;
+    if (i < n) {
+      y = start_y + i / bw;
+      x = start_x + i % bw;
+      const float m = cached ? s_mag[i] : grad_mag(bl, W, y, x);
+      f = m > block_th;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[wid] = __popc(mk);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kSelThreads / 32; k++) {
+      if (k < wid) woff += s_w[k];
+      tot += s_w[k];
+    }
+    const int rank = run + woff + __popc(mk & ((1u << lane) - 1u));
+    if (f && rank < kSelMax) {
+      val[(int64_t)y * W + x] = 1;
+      d.sel_xy[((int64_t)b * kGridBlocks + block_id) * kSelMax + rank] = (y << 16) | x;
+    }
+    run += tot;
+    __syncthreads();
+  }
+  const int cnt = min(run, kSelMax);
+  if (threadIdx.x < kSelMax && threadIdx.x >= cnt)  // unfilled slots of this block's list
+    d.sel_xy[((int64_t)b * kGridBlocks + block_id) * kSelMax + threadIdx.x] = -1;
+  if (threadIdx.x == 0) {
+    d.sel_count[b * kGridBlocks + block_id] = cnt;
+    atomicAdd(&d.stats[b].n_selected, cnt);
+  }
+}
+
+// ---- disparity line search ----------------------------------------------------------------------------
+constexpr int kSegW = 64;
+constexpr int kDispThreads = 256;
+
+__global__ void __launch_bounds__(kDispThreads) k_disparity(int W, int H, odo_depth_params p, DepthWork d) {
+  extern __shared__ float s_rows[];  // [5][pitch] right rows y-2 .. y+2
+  const int b = blockIdx.z;
+  const int bnd = p.boundary;
+  const int y = bnd + blockIdx.y;
+  const int x0 = bnd + kSegW * blockIdx.x;
+  const int64_t npx = (int64_t)W * H;
+  const uint8_t* val = d.val + b * npx + (int64_t)y * W;
+  __shared__ unsigned s_mask[2];
+  if (threadIdx.x < 64) {
+    const int x = x0 + threadIdx.x;
+    const bool sel = (x < W - bnd) && (val[x] != 0);
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = m;
+  }
+  __syncthreads();
+  const unsigned m0 = s_mask[0], m1 = s_mask[1];
+  if ((m0 | m1) == 0u) return;
+  const int xmax = x0 + (m1 ? 63 - __clz(m1) : 31 - __clz(m0));
+  const int pitch = W;
+  // stage columns [0, xmax + 2] (candidates end at xmax-1, taps reach +2) of the five right rows
+  const int ncol = min(xmax + 3, W);
+  const float* br = d.blurR + b * npx;
+  for (int r = 0; r < 5; r++) {
+    const float* src = br + (int64_t)(y - 2 + r) * W;
+    float* dst = s_rows + r * pitch;
+    for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const float* rpp = s_rows;
+  const float* rp = s_rows + pitch;
+  const float* rc = s_rows + 2 * pitch;
+  const float* rn = s_rows + 3 * pitch;
+  const float* rnn = s_rows + 4 * pitch;
+  const float* bl = d.blurL + b * npx;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int count = __popc(m0) + __popc(m1);
+  for (int k = wid; k < count; k += kDispThreads / 32) {
+    // x of the k-th selected pixel of the segment
+    int x;
+    {
+      const int c0 = __popc(m0);
+      unsigned m = (k < c0) ? m0 : m1;
+      int kk = (k < c0) ? k : k - c0;
+      for (int j = 0; j < kk; j++) m &= m - 1u;
+      x = x0 + ((k < c0) ? 0 : 32) + (__ffs(m) - 1);
+    }
+    // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
+    const float l0 = __ldg(bl + (int64_t)(y + 2) * W + x), l1 = __ldg(bl + (int64_t)(y + 1) * W + x - 1),
+                l2 = __ldg(bl + (int64_t)y * W + x + 2), l3 = __ldg(bl + (int64_t)y * W + x),
+                l4 = __ldg(bl + (int64_t)y * W + x - 2), l5 = __ldg(bl + (int64_t)(y - 1) * W + x + 1),
+                l6 = __ldg(bl + (int64_t)(y - 1) * W + x - 1), l7 = __ldg(bl + (int64_t)(y - 2) * W + x);
+    float best = 1e+10f;
+    int best_rx = -1;
+#pragma unroll 2
+    for (int rx = bnd + lane; rx < x; rx += 32) {
+      // ComputeSsdPattern8Sse (:435-453): sub, mul, hadd, hadd, movehl+add
+      float d0 = __fsub_rn(l0, rnn[rx]), d1 = __fsub_rn(l1, rn[rx - 1]), d2 = __fsub_rn(l2, rc[rx + 2]),
+            d3 = __fsub_rn(l3, rc[rx]), d4 = __fsub_rn(l4, rc[rx - 2]), d5 = __fsub_rn(l5, rp[rx + 1]),
+            d6 = __fsub_rn(l6, rp[rx - 1]), d7 = __fsub_rn(l7, rpp[rx]);
+      d0 = __fmul_rn(d0, d0); d1 = __fmul_rn(d1, d1); d2 = __fmul_rn(d2, d2); d3 = __fmul_rn(d3, d3);
+      d4 = __fmul_rn(d4, d4); d5 = __fmul_rn(d5, d5); d6 = __fmul_rn(d6, d6); d7 = __fmul_rn(d7, d7);
+      const float ssd = __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)),
+                                  __fadd_rn(__fadd_rn(d4, d5), __fadd_rn(d6, d7)));
+      if (ssd < best) {  // strict '<' in ascending rx: first minimum wins (:385-386)
+        best = ssd;
+        best_rx = rx;
+      }
+    }
+    // warp argmin: smaller cost, ties to the smaller column
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int orx = __shfl_xor_sync(0xffffffffu, best_rx, o);
+      const bool take = (orx >= 0) && (best_rx < 0 || ob < best || (ob == best && orx < best_rx));
+      if (take) {
+        best = ob;
+        best_rx = orx;
+      }
+    }
+    if (lane == 0) {
+      const int64_t o = b * npx + (int64_t)y * W + x;
+      if (d.min_ssd) d.min_ssd[o] = best;
+      if (!(best > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+        const float disp = (float)abs(x - best_rx);
+        d.disp[o] = disp;
+        d.dep[o] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+        if (d.match_x) d.match_x[o] = best_rx;
+        atomicAdd(&d.stats[b].n_matched, 1);
+      }
+    }
+  }
+}
+
+// ---- inverse-depth refinement ---------------------------------------------------------------------------
+constexpr int kRefThreads = 512;
+constexpr int kRefWarps = kRefThreads / 32;
+
+struct RefShared {
+  double warp[kRefWarps][32];
+  double tot[32];
+};
+
+__global__ void __launch_bounds__(kRefThreads, 1) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
+                                                          int64_t stride, int W, int H, odo_depth_params p,
+                                                          DepthWork d, double* partials, unsigned* barrier,
+                                                          int* abort_flag) {
+  __shared__ RefShared sh;
+  const int b = blockIdx.y;
+  const int G = gridDim.x;
+  GroupSync gs;
+  gs.partials = partials + (int64_t)b * 2 * G * 32;
+  gs.counter = barrier + b;
+  gs.abort_flag = abort_flag;
+  gs.target = 0;
+  gs.parity = 0;
+  gs.G = G;
+  const int64_t npx = (int64_t)W * H;
+  const float* L = Limg + b * stride;
+  const float* R = Rimg + b * stride;
+  float* dep = d.dep + b * npx;
+  uint8_t* val = d.val + b * npx;
+  // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
+  const int nslots = d.cap;
+  const int* sel_xy = d.sel_xy + (int64_t)b * nslots;
+  float* st_cur = d.ref_state + (int64_t)b * 6 * nslots;
+  float* st_pre = st_cur + nslots;
+  float* st_tmp = st_pre + nslots;
+  float* st_res = st_tmp + nslots;
+  float* st_jt = st_res + nslots;
+  float* st_bv = st_jt + nslots;
+  odo_depth_stats* stats = d.stats + b;
+  const int tid = blockIdx.x * kRefThreads + threadIdx.x;
+  const int nthreads = G * kRefThreads;
+  const int n_sel = stats->n_selected;  // written by k_select (previous launch)
+  const bool too_many = n_sel > p.max_residuals;  // quirk Q7: the reference would overflow init_depth
+
+  // init: init_depth / current_depth / tmp_depth, :105-139
+  for (int s = tid; s < nslots; s += nthreads) {
+    const int yx = sel_xy[s];
+    if (yx < 0) continue;
+    const float v = dep[(int64_t)(yx >> 16) * W + (yx & 0xffff)];
+    st_cur[s] = v;
+    st_tmp[s] = v;
+    st_pre[s] = 0.f;
+    st_res[s] = 0.f;
+  }
+  float lambda = p.lambda;
+  float err_last = 1e+10f, err_now = 0.f;
+  int iter_count = 0;
+  const float txfx = __fmul_rn(p.baseline, p.fx);  // tx * fx
+  const float gscale = __fmul_rn(txfx, 0.5f);
+  while (!too_many && p.max_iters > iter_count) {
+    // ComputeResidualJacobian(tmp_depth), :200-242
+    double acc[2] = {0.0, 0.0};
+    for (int s = tid; s < nslots; s += nthreads) {
+      const int yx = sel_xy[s];
+      if (yx < 0) continue;
+      const int y = yx >> 16, x = yx & 0xffff;
+      const float wf = floorf(__fsub_rn((float)x, __fmul_rn(txfx, st_tmp[s])));
+      if (!(wf >= 2.0f && wf <= (float)(W - 2))) {  // also catches NaN (int(NaN) is INT_MIN on x86)
+        st_jt[s] = 0.f;
+        st_bv[s] = 0.f;
+        st_res[s] = -1000.f;
+        continue;
+      }
+      const int wx = (int)wf;
+      const float* rrow = R + (int64_t)y * W;
+      const float r_i = __fsub_rn(__ldg(L + (int64_t)y * W + x), __ldg(rrow + wx));
+      const float ar = fabsf(r_i);
+      const float w_i = (ar <= p.huber_delta) ? 1.0f : __fdiv_rn(p.huber_delta, ar);
+      const float g = __fmul_rn(gscale, __fsub_rn(__ldg(rrow + wx + 1), __ldg(rrow + wx - 1)));
+      st_res[s] = ar;
+      acc[0] += (double)__fmul_rn(__fmul_rn(r_i, r_i), w_i);
+      acc[1] += 1.0;
+      st_jt[s] = __fmul_rn(__fmul_rn(g, g), w_i);
+      st_bv[s] = __fmul_rn(__fmul_rn(-g, w_i), r_i);
+    }
+    group_allreduce<2, kRefWarps>(acc, sh.warp, sh.tot, gs);
+    err_now = (float)(sh.tot[0] / sh.tot[1]);
+    __syncthreads();
+    if (*(volatile int*)abort_flag) break;
+    bool reject = false, stop = false;
+    if (err_now > err_last) {  // :147-151
+      lambda = lambda * 10.0f;
+      if (lambda > 1e+5f) break;
+      reject = true;
+    } else {                   // :152-159
+      const float err_diff = err_now / err_last;
+      if (err_diff > p.precision) stop = true;
+      else {
+        err_last = err_now;
+        lambda = fmaxf(lambda / 10.0f, 1e-7f);
+      }
+    }
+    for (int s = tid; s < nslots; s += nthreads) {
+      if (sel_xy[s] < 0) continue;
+      float cur;
+      if (reject) {
+        cur = st_pre[s];
+      } else {
+        cur = st_tmp[s];
+        st_pre[s] = cur;
+      }
+      st_cur[s] = cur;
+      if (!stop) {
+        // A = jtwj + lambda*jtwj ; delta = A.inverse() * b ; tmp = delta + current, :162-165
+        const float jt = st_jt[s];
+        const float A = __fadd_rn(jt, __fmul_rn(lambda, jt));
+        const float delta = __fmul_rn(__fdiv_rn(1.0f, A), st_bv[s]);
+        st_tmp[s] = __fadd_rn(delta, cur);
+      }
+    }
+    if (stop) break;
+    iter_count++;
+  }
+  // write-back and filters, :176-191
+  double nv[1] = {0.0};
+  for (int s = tid; s < nslots && !too_many; s += nthreads) {
+    const int yx = sel_xy[s];
+    if (yx < 0) continue;
+    const int64_t o = (int64_t)(yx >> 16) * W + (yx & 0xffff);
+    const float res = st_res[s], cur = st_cur[s];
+    bool ok;
+    if (res > p.photo_th || res == -1000.f) ok = false;
+    else {
+      const float z = __fdiv_rn(1.0f, cur);
+      ok = !(z > p.max_depth || z < p.min_depth);
+    }
+    val[o] = ok ? 1 : 0;
+    dep[o] = ok ? cur : 0.f;
+    nv[0] += ok ? 1.0 : 0.0;
+  }
+  group_allreduce<1, kRefWarps>(nv, sh.warp, sh.tot, gs);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int n_valid = (int)sh.tot[0];
+    stats->n_valid = n_valid;
+    stats->iters = iter_count;
+    stats->cost = err_now;
+    int status = (n_valid < 500) ? -1 : 0;  // :192-197
+    if (too_many || *(volatile int*)abort_flag) status = -1;
+    stats->status = status;
+  }
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------
+static size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t depth_work_bytes(int w, int h, int batch, bool debug) {
+  const size_t npx = (size_t)w * h * batch;
+  size_t bytes = 0;
+  bytes += al(npx * 4) * 4;              // blurL, blurR, disp, dep
+  bytes += al(npx);                      // val
+  if (debug) bytes += al(npx * 4) * 2;   // match_x, min_ssd
+  bytes += al((size_t)batch * kGridBlocks * kSelMax * 4);       // sel_xy
+  bytes += al((size_t)batch * kGridBlocks * 4);                 // sel_count
+  bytes += al((size_t)batch * sizeof(odo_depth_stats));
+  bytes += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);   // refinement state
+  return bytes;
+}
+
+int depth_slots() { return kGridBlocks * kSelMax; 
+}
+
+void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debug) {
+  const size_t npx = (size_t)w * h * batch;
+  char* p = (char*)mem;
+  d->blurL = (float*)p; p += al(npx * 4);
+  d->blurR = (float*)p; p += al(npx * 4);
+  d->disp = (float*)p; p += al(npx * 4);
+  d->dep = (float*)p; p += al(npx * 4);
+  d->val = (uint8_t*)p; p += al(npx);
+  d->match_x = nullptr;
+  d->min_ssd = nullptr;
+  if (debug) {
+    d->match_x = (int*)p; p += al(npx * 4);
+    d->min_ssd = (float*)p; p += al(npx * 4);
+  }
+  d->sel_xy = (int*)p; p += al((size_t)batch * kGridBlocks * kSelMax * 4);
+  d->sel_count = (int*)p; p += al((size_t)batch * kGridBlocks * 4);
+  d->stats = (odo_depth_stats*)p; p += al((size_t)batch * sizeof(odo_depth_stats));
+  d->ref_state = (float*)p;
+  d->cap = kGridBlocks * kSelMax;
+}
+
+void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+                   const odo_depth_params& p, DepthWork d, int batch) {
+  const size_t npx = (size_t)w * h;
+  // cv::GaussianBlur on both images, :255-257 ; outputs zero-filled (quirk Q6)
+  launch_blur3(c, L, stride, d.blurL, (int64_t)npx, w, h, batch);
+  launch_blur3(c, R, stride, d.blurR, (int64_t)npx, w, h, batch);
+  cudaMemsetAsync(d.val, 0, npx * batch, c->stream);
+  cudaMemsetAsync(d.disp, 0, npx * batch * 4, c->stream);
+  cudaMemsetAsync(d.dep, 0, npx * batch * 4, c->stream);
+  cudaMemsetAsync(d.stats, 0, sizeof(odo_depth_stats) * batch, c->stream);
+  if (d.match_x) cudaMemsetAsync(d.match_x, 0xff, npx * batch * 4, c->stream);
+  if (d.min_ssd) cudaMemsetAsync(d.min_ssd, 0, npx * batch * 4, c->stream);
+  k_select<<<dim3(kGridBlocks, batch), kSelThreads, 0, c->stream>>>(w, h, p, d);
+  c->launches++;
+}
+
+void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
+  const int rows = h - 2 * p.boundary;
+  const int segs = (w - 2 * p.boundary + kSegW - 1) / kSegW;
+  if (rows <= 0 || segs <= 0) return;
+  const size_t smem = sizeof(float) * 5 * (size_t)w;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(k_disparity, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  k_disparity<<<dim3(segs, rows, batch), kDispThreads, smem, c->stream>>>(w, h, p, d);
+  c->launches++;
+}
+
+// scratch for the refinement's group reduction lives behind the refinement state
+void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+                         const odo_depth_params& p, DepthWork d, int batch) {
+  int G = c->sm_count / (batch > 0 ? batch : 1);
+  const int gmax = (kGridBlocks * kSelMax + kRefThreads - 1) / kRefThreads;  // one slot per thread
+  if (G > gmax) G = gmax;
+  if (G < 1) G = 1;
+  // partials / barrier / abort flag: carved from a small dedicated allocation owned by the context
+  const size_t need = al(sizeof(double) * 2 * (size_t)G * 32 * batch) + al(sizeof(unsigned) * batch) + 256;
+  if (c->scratch_bytes[15] < need) {
+    if (c->scratch[15]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[15]); }
+    c->scratch[15] = nullptr;
+    c->scratch_bytes[15] = 0;
+    if (cudaMalloc(&c->scratch[15], need) != cudaSuccess) { c->err = "cudaMalloc failed"; return; }
+    c->scratch_bytes[15] = need;
+  }
+  char* q = (char*)c->scratch[15];
+  double* partials = (double*)q; q += al(sizeof(double) * 2 * (size_t)G * 32 * batch);
+  unsigned* barrier = (unsigned*)q; q += al(sizeof(unsigned) * batch);
+  int* abort_flag = (int*)q;
+  cudaMemsetAsync(barrier, 0, al(sizeof(unsigned) * batch) + 256, c->stream);
+  dim3 grid(G, batch), block(kRefThreads);
+  cudaError_t e;
+  if (G > 1) {
+    int W = w, H = h;
+    int64_t st = stride;
+    odo_depth_params pp = p;
+    void* args[] = {(void*)&L, (void*)&R, (void*)&st, (void*)&W, (void*)&H, (void*)&pp, (void*)&d,
+                    (void*)&partials, (void*)&barrier, (void*)&abort_flag};
+    e = cudaLaunchCooperativeKernel((const void*)k_refine, grid, block, args, 0, c->stream);
+  } else {
+    k_refine<<<grid, block, 0, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) c->err = std::string("k_refine launch: ") + cudaGetErrorString(e);
+  c->launches++;
+}

@@ -1,0 +1,84 @@
+// group_sync.cuh -- deterministic reduction across the G CTAs that cooperate on one sequence.
+//
+// Each CTA reduces its values with a fixed shuffle tree and a fixed-order sum over warps, publishes
+// the partial in a double-buffered global array, meets the other CTAs of its group at a counter
+// barrier and then sums the G partials in index order.  Every CTA ends up with bit-identical totals,
+// so the replicated control flow (accept/reject, convergence) stays in lock step without a second
+// barrier.  G == 1 never touches global memory.  Kernels using G > 1 are launched cooperatively so
+// that all CTAs of a group are co-resident.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct GroupSync {
+  double* partials;     // this sequence: [2][G][32]
+  unsigned* counter;    // this sequence, zeroed before the launch
+  int* abort_flag;
+  unsigned target;      // barrier generation target (meaningful in thread 0)
+  int parity;
+  int G;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all CTAs of the group arrive, then proceed; the spin is bounded so a lost CTA cannot hang the device
+__device__ __forceinline__ void group_barrier(GroupSync& gs) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    gs.target += (unsigned)gs.G;
+    __threadfence();
+    atomicAdd(gs.counter, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(gs.counter) < gs.target) {
+      ++spins;
+      if ((spins & 1023u) == 0u && *(volatile int*)gs.abort_flag) break;
+      if (spins > (1u << 21)) {
+        atomicExch(gs.abort_flag, 1);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sums vals[0..NV) over all threads of all G CTAs of the sequence in a fixed order; the totals end up
+// in s_tot[0..NV) of every CTA.  s_warp: [WARPS][32] doubles of shared memory.
+template <int NV, int WARPS>
+__device__ __forceinline__ void group_allreduce(double* vals, double (*s_warp)[32], double* s_tot, GroupSync& gs) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_warp[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) s += s_warp[w][threadIdx.x];
+    if (gs.G == 1) {
+      s_tot[threadIdx.x] = s;
+    } else {
+      __stcg(gs.partials + ((int64_t)gs.parity * gs.G + blockIdx.x) * 32 + threadIdx.x, s);
+    }
+  }
+  if (gs.G > 1) {
+    group_barrier(gs);
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+      const double* p = gs.partials + (int64_t)gs.parity * gs.G * 32 + threadIdx.x;
+      for (int c = 0; c < gs.G; c++) s += __ldcg(p + (int64_t)c * 32);
+      s_tot[threadIdx.x] = s;
+    }
+    gs.parity ^= 1;
+  }
+  __syncthreads();
+}

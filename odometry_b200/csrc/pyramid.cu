@@ -1,0 +1,208 @@
+// pyramid.cu -- image / inverse-depth pyramid kernels (sm_100a).
+//
+// Replaces GaussianImagePyramidNaive (src/image_processing_global.cpp:12-56: cv::GaussianBlur 3x3 for
+// level 0, cv::pyrDown of the RAW input for level 1, cv::pyrDown chain above) and
+// MedianDepthPyramidNaive (src/image_processing_global.cpp:58-113: copy / 3x3 median, then odd-pixel
+// subsampling).  The floating-point association of every output pixel follows OpenCV's kernels
+// (separable [1 2 1]/4 as b*0.5 + (a+c)*0.25; pyrDown's SIMD-body / scalar-tail split by column, see
+// DESIGN.md "K1") so the levels are bit-identical to cv2 4.13.0 -- the file is compiled with
+// -fmad=false and uses explicit round-to-nearest intrinsics where the order matters.
+//
+// HBM-bound streaming stencils: one thread per output pixel, the 3x3 / 5x5 footprint is served by
+// L1/L2 (each input line is fetched from HBM once), batch index on blockIdx.z.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  // cv::borderInterpolate(BORDER_REFLECT_101); |offsets| <= 2 and len >= 2 here, one bounce suffices
+  if (len == 1) return 0;
+  if (p < 0) p = -p;
+  if (p >= len) p = 2 * len - 2 - p;
+  if (p < 0) p = -p;
+  return p;
+}
+
+__global__ void k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  // gray_8u.convertTo(gray, CV_32F), run_odometry_kitti_offline.cpp:348,358 ; 4 pixels per thread
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const uchar4 v = *reinterpret_cast<const uchar4*>(src + i);
+    *reinterpret_cast<float4*>(dst + i) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  } else {
+    for (int64_t k = i; k < n; k++) dst[k] = (float)src[k];
+  }
+}
+
+__device__ __forceinline__ float tap121(float a, float b, float c) {
+  // s[0]*k0 + (s[-1] + s[+1])*k1 with k = [0.25 0.5 0.25]
+  return __fadd_rn(__fmul_rn(b, 0.5f), __fmul_rn(__fadd_rn(a, c), 0.25f));
+}
+
+// cv::GaussianBlur(src, dst, Size(3,3), 0), CV_32F, BORDER_REFLECT_101
+__global__ void __launch_bounds__(256) k_blur3(const float* __restrict__ src, int64_t sstride,
+                                               float* __restrict__ dst, int64_t dstride, int w, int h) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const float* s = src + (int64_t)blockIdx.z * sstride;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+  const float* r0 = s + (int64_t)ym * w;
+  const float* r1 = s + (int64_t)y * w;
+  const float* r2 = s + (int64_t)yp * w;
+  const float t0 = tap121(__ldg(r0 + xm), __ldg(r0 + x), __ldg(r0 + xp));
+  const float t1 = tap121(__ldg(r1 + xm), __ldg(r1 + x), __ldg(r1 + xp));
+  const float t2 = tap121(__ldg(r2 + xm), __ldg(r2 + x), __ldg(r2 + xp));
+  dst[(int64_t)blockIdx.z * dstride + (int64_t)y * w + x] = tap121(t0, t1, t2);
+}
+
+// horizontal 1-4-6-4-1 of one source row at even column 2x (unscaled)
+__device__ __forceinline__ float hrow5(const float* __restrict__ r, int i0, int i1, int i2, int i3, int i4,
+                                       bool body) {
+  const float s0 = __ldg(r + i0), s1 = __ldg(r + i1), s2 = __ldg(r + i2), s3 = __ldg(r + i3), s4 = __ldg(r + i4);
+  if (body)  // v_muladd(r2, 6, v_muladd(r1 + r3, 4, r0 + r4))
+    return __fadd_rn(__fmul_rn(s2, 6.f), __fadd_rn(__fmul_rn(__fadd_rn(s1, s3), 4.f), __fadd_rn(s0, s4)));
+  // src[2x]*6 + (src[2x-1] + src[2x+1])*4 + src[2x-2] + src[2x+2], left to right
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s2, 6.f), __fmul_rn(__fadd_rn(s1, s3), 4.f)), s0), s4);
+}
+
+// cv::pyrDown(src, dst, Size(dw, dh)), CV_32F, BORDER_REFLECT_101 (OpenCV pyrDown_<FltCast<float,8>>)
+__global__ void __launch_bounds__(256) k_pyrdown(const float* __restrict__ src, int64_t sstride, int sw, int sh,
+                                                 float* __restrict__ dst, int64_t dstride, int dw, int dh,
+                                                 int hbody_end, int vbody_end) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  const float* s = src + (int64_t)blockIdx.z * sstride;
+  const int i0 = reflect101(2 * x - 2, sw), i1 = reflect101(2 * x - 1, sw), i2 = reflect101(2 * x, sw),
+            i3 = reflect101(2 * x + 1, sw), i4 = reflect101(2 * x + 2, sw);
+  const bool hbody = (x >= 1) && (x < hbody_end);
+  float r[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const int sy = reflect101(2 * y - 2 + k, sh);
+    r[k] = hrow5(s + (int64_t)sy * sw, i0, i1, i2, i3, i4, hbody);
+  }
+  float v;
+  if (x < vbody_end)  // v_muladd((r1 + r3) + r2, 4, (r0 + r4) + (r2 + r2))
+    v = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(r[1], r[3]), r[2]), 4.f),
+                  __fadd_rn(__fadd_rn(r[0], r[4]), __fadd_rn(r[2], r[2])));
+  else  // row2*6 + (row1 + row3)*4 + row0 + row4
+    v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[2], 6.f), __fmul_rn(__fadd_rn(r[1], r[3]), 4.f)), r[0]), r[4]);
+  dst[(int64_t)blockIdx.z * dstride + (int64_t)y * dw + x] = __fmul_rn(v, 1.f / 256.f);
+}
+
+__global__ void k_copy_batched(const float* __restrict__ src, int64_t sstride, float* __restrict__ dst,
+                               int64_t dstride, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(int64_t)blockIdx.y * dstride + i] = __ldg(src + (int64_t)blockIdx.y * sstride + i);
+}
+
+__device__ __forceinline__ void cswap(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
+
+// cv::medianBlur(src, dst, 3) on CV_32F, BORDER_REPLICATE (dead path for all reference callers)
+__global__ void k_median3(const float* __restrict__ src, int64_t sstride, float* __restrict__ dst,
+                          int64_t dstride, int w, int h) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const float* s = src + (int64_t)blockIdx.z * sstride;
+  float v[9];
+  int k = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; dy++) {
+    const int yy = min(max(y + dy, 0), h - 1);
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) v[k++] = __ldg(s + (int64_t)yy * w + min(max(x + dx, 0), w - 1));
+  }
+  // 19-exchange median-of-9 network
+  cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+  cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+  cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+  cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+  cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+  cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+  cswap(v[4], v[2]);
+  dst[(int64_t)blockIdx.z * dstride + (int64_t)y * w + x] = v[4];
+}
+
+// levels 1.. of the depth pyramid straight from level 0:
+//   Ll(y,x) = L(l-1)(2y+1, 2x+1)  =>  Ll(y,x) = L0(2^l y + 2^l - 1, 2^l x + 2^l - 1)
+__global__ void k_depth_levels(float* __restrict__ pyr, int64_t pstride, PyrGeom g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + g.off[1];
+  if (i >= g.total) return;
+  int l = 1;
+  while (l + 1 < g.levels && i >= g.off[l + 1]) l++;
+  const int64_t r = i - g.off[l];
+  const int y = (int)(r / g.w[l]), x = (int)(r % g.w[l]);
+  const int s = (1 << l) - 1;
+  float* p = pyr + (int64_t)blockIdx.y * pstride;
+  p[i] = p[(int64_t)((y << l) + s) * g.w[0] + ((x << l) + s)];
+}
+
+}  // namespace
+
+void launch_u8_to_f32(odo_ctx* c, const uint8_t* src, float* dst, int64_t n) {
+  const int64_t nthreads = (n + 3) / 4;
+  k_u8_to_f32<<<(unsigned)((nthreads + 255) / 256), 256, 0, c->stream>>>(src, dst, n);
+  c->launches++;
+}
+
+void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch) {
+  dim3 grid((w + 31) / 32, (h + 7) / 8, batch), block(32, 8);
+  k_blur3<<<grid, block, 0, c->stream>>>(src, sstride, dst, dstride, w, h);
+  c->launches++;
+}
+
+void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
+                    int dw, int dh, int batch) {
+  // column split of OpenCV's pyrDown_ for a 4-lane (SSE-baseline) build, see oracle/imgproc.cpp
+  const int lanes = 4;
+  int width0 = (sw - 2 - 1) / 2 + 1;
+  if (width0 > dw) width0 = dw;
+  const int hbody_end = (width0 > 1) ? 1 + lanes * ((width0 - 1) / lanes) : 1;
+  const int vbody_end = lanes * (dw / lanes);
+  dim3 grid((dw + 31) / 32, (dh + 7) / 8, batch), block(32, 8);
+  k_pyrdown<<<grid, block, 0, c->stream>>>(src, sstride, sw, sh, dst, dstride, dw, dh, hbody_end, vbody_end);
+  c->launches++;
+}
+
+void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
+                          const PyrGeom& g, int smooth, int batch) {
+  const int64_t n0 = (int64_t)g.w[0] * g.h[0];
+  if (smooth) {
+    launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch);
+  } else {
+    dim3 grid((unsigned)((n0 + 255) / 256), batch);
+    k_copy_batched<<<grid, 256, 0, c->stream>>>(img, istride, pyr, pstride, n0);
+    c->launches++;
+  }
+  if (g.levels > 1)  // level 1 from the RAW input (quirk Q5)
+    launch_pyrdown(c, img, istride, g.w[0], g.h[0], pyr + g.off[1], pstride, g.w[1], g.h[1], batch);
+  for (int l = 2; l < g.levels; l++)
+    launch_pyrdown(c, pyr + g.off[l - 1], pstride, g.w[l - 1], g.h[l - 1], pyr + g.off[l], pstride, g.w[l], g.h[l], batch);
+}
+
+void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,
+                          const PyrGeom& g, int smooth, int batch) {
+  const int64_t n0 = (int64_t)g.w[0] * g.h[0];
+  if (smooth) {
+    dim3 grid((g.w[0] + 31) / 32, (g.h[0] + 7) / 8, batch), block(32, 8);
+    k_median3<<<grid, block, 0, c->stream>>>(dep, dstride, pyr, pstride, g.w[0], g.h[0]);
+  } else {
+    dim3 grid((unsigned)((n0 + 255) / 256), batch);
+    k_copy_batched<<<grid, 256, 0, c->stream>>>(dep, dstride, pyr, pstride, n0);
+  }
+  c->launches++;
+  if (g.levels > 1) {
+    const int64_t rest = g.total - g.off[1];
+    dim3 grid((unsigned)((rest + 255) / 256), batch);
+    k_depth_levels<<<grid, 256, 0, c->stream>>>(pyr, pstride, g);
+    c->launches++;
+  }
+}

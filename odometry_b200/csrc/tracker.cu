@@ -1,0 +1,519 @@
+// tracker.cu -- batched, device-resident tracking loop (sm_100a) and the depth entry points.
+//
+// The per-frame control flow of run_odometry_kitti_offline.cpp:95-271 for n_seq independent stereo
+// sequences advanced in lock step.  Everything a frame needs stays on the device: the keyframe
+// pyramids and their LM point lists, the warm-start pose, the absolute keyframe pose.  Per step the
+// host only uploads the n_seq stereo pairs and reads back the poses; the keyframe decision
+// (run_odometry_kitti_offline.cpp:254-270) is taken on the device.
+#include "common.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct SeqState {
+  float kf_pose_abs[16];   // keyframe_poses_abs[current_kf]
+  float cur_pose[16];
+  float pose_kf[16];       // pose_to_keyframe of the last frame
+  float motion;
+  int promote;             // this frame becomes the keyframe
+  int dead;                // depth failed earlier: the reference `break`s out of its loop
+  int status;
+  int lm_status;
+};
+
+// Eigen Matrix4f::inverse(): general inverse, evaluated in double and rounded (as oracle/tracker.cpp)
+__device__ void inverse4(const float* M, float* out) {
+  double a[4][8];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      a[r][c] = M[c * 4 + r];
+      a[r][4 + c] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 4; r++)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (piv != c)
+      for (int k = 0; k < 8; k++) { const double t = a[c][k]; a[c][k] = a[piv][k]; a[piv][k] = t; }
+    const double d = a[c][c];
+    for (int k = 0; k < 8; k++) a[c][k] = __ddiv_rn(a[c][k], d);
+    for (int r = 0; r < 4; r++)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int k = 0; k < 8; k++) a[r][k] = __dsub_rn(a[r][k], __dmul_rn(f, a[c][k]));
+      }
+  }
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) out[c * 4 + r] = (float)a[r][4 + c];
+}
+
+__device__ void mat4_mul_fma(const float* A, const float* B, float* C) {
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) {
+      float r = __fmul_rn(A[i], B[4 * j]);
+      r = __fmaf_rn(A[4 + i], B[4 * j + 1], r);
+      r = __fmaf_rn(A[8 + i], B[4 * j + 2], r);
+      r = __fmaf_rn(A[12 + i], B[4 * j + 3], r);
+      C[4 * j + i] = r;
+    }
+}
+
+// motion magnitude, run_odometry_kitti_offline.cpp:145,254-257 (Sophus SO3::angleX/Y/Z, so3.hpp:127-154)
+__device__ float motion_magnitude(const float* T) {
+  float R[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i][j] = T[j * 4 + i];
+  // Sophus::SO3<float>(R).matrix(): matrix -> quaternion -> matrix
+  float q[4];
+  {
+    float t = R[0][0] + R[1][1] + R[2][2];
+    if (t > 0.f) {
+      t = sqrtf(t + 1.0f);
+      q[0] = 0.5f * t;
+      t = 0.5f / t;
+      q[1] = (R[2][1] - R[1][2]) * t;
+      q[2] = (R[0][2] - R[2][0]) * t;
+      q[3] = (R[1][0] - R[0][1]) * t;
+    } else {
+      int i = 0;
+      if (R[1][1] > R[0][0]) i = 1;
+      if (R[2][2] > R[i][i]) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = sqrtf(R[i][i] - R[j][j] - R[k][k] + 1.0f);
+      q[1 + i] = 0.5f * t;
+      t = 0.5f / t;
+      q[0] = (R[k][j] - R[j][k]) * t;
+      q[1 + j] = (R[j][i] + R[i][j]) * t;
+      q[1 + k] = (R[k][i] + R[i][k]) * t;
+    }
+  }
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  const float r00 = 1.f - (tyy + tzz), r01 = txy - twz, r02 = txz + twy;
+  const float r10 = txy + twz, r11 = 1.f - (txx + tzz), r12 = tyz - twx;
+  const float r20 = txz - twy, r21 = tyz + twx, r22 = 1.f - (txx + tyy);
+  const float ax = (float)atan2((double)(r21 - r12), (double)(r11 + r22));
+  const float ay = (float)atan2((double)(r02 - r20), (double)(r00 + r22));
+  const float az = (float)atan2((double)(r10 - r01), (double)(r00 + r11));
+  const float mot[6] = {fabsf(ax), fabsf(ay), fabsf(az), fabsf(T[12]), fabsf(T[13]), fabsf(T[14])};
+  const float wgt[6] = {0.1f / 3.3f, 1.0f / 3.3f, 0.1f / 3.3f, 1.0f / 3.3f, 0.1f / 3.3f, 1.0f / 3.3f};
+  float s = 0.f;
+  for (int i = 0; i < 6; i++) s += mot[i] * wgt[i];
+  return s;
+}
+
+__global__ void k_track_init(SeqState* st, float* T_init, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  SeqState& s = st[b];
+  for (int i = 0; i < 16; i++) {
+    const float v = (i % 5 == 0) ? 1.f : 0.f;
+    s.kf_pose_abs[i] = v;
+    s.cur_pose[i] = v;
+    s.pose_kf[i] = v;
+    T_init[b * 16 + i] = v;
+  }
+  s.motion = 0.f;
+  s.promote = 0;
+  s.dead = 0;
+  s.status = 0;
+  s.lm_status = 0;
+}
+
+// after Solve: cur_pose = kf_pose_abs * T^-1 (:218), motion magnitude and keyframe vote (:254-258),
+// Reset(pose_to_keyframe, 0.01f) = warm start for the next frame (:261,:268)
+__global__ void k_track_pose(SeqState* st, const LmResult* res, float* T_init, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  SeqState& s = st[b];
+  if (s.dead) return;
+  const float* T = res[b].T;
+  float Tinv[16];
+  inverse4(T, Tinv);
+  mat4_mul_fma(s.kf_pose_abs, Tinv, s.cur_pose);
+  for (int i = 0; i < 16; i++) {
+    s.pose_kf[i] = T[i];
+    T_init[b * 16 + i] = T[i];
+  }
+  s.lm_status = res[b].status;
+  s.motion = motion_magnitude(T);
+  s.promote = (s.motion > 1.1f) ? 1 : 0;
+}
+
+// after ComputeDepth: a failed depth ends the sequence (:230-232); a promoted frame takes over the
+// absolute keyframe pose (:259-260)
+__global__ void k_track_finalize(SeqState* st, const odo_depth_stats* ds, int* promote_flags, int first, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  SeqState& s = st[b];
+  if (s.dead) {
+    promote_flags[b] = 0;
+    s.promote = 0;
+    s.status = -1;
+    return;
+  }
+  if (ds[b].status != 0) {
+    s.dead = 1;
+    s.promote = 0;
+    s.status = -1;
+    promote_flags[b] = 0;
+    return;
+  }
+  if (first) s.promote = 1;
+  promote_flags[b] = s.promote;
+  s.status = 0;
+  if (s.promote)
+    for (int i = 0; i < 16; i++) s.kf_pose_abs[i] = s.cur_pose[i];
+}
+
+__global__ void k_promote_copy(const float* __restrict__ src, float* __restrict__ dst, int64_t n,
+                               const int* __restrict__ flags) {
+  if (!flags[blockIdx.y]) return;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t o = (int64_t)blockIdx.y * n;
+  if (i + 3 < n) {
+    *reinterpret_cast<float4*>(dst + o + i) = *reinterpret_cast<const float4*>(src + o + i);
+  } else {
+    for (int64_t k = i; k < n; k++) dst[o + k] = src[o + k];
+  }
+}
+
+}  // namespace
+
+struct odo_tracker {
+  odo_ctx* c = nullptr;
+  int w = 0, h = 0, levels = 0, n = 0;
+  PyrGeom g;
+  odo_lm_params lm;
+  odo_depth_params dp;
+  int64_t npx = 0;
+  int64_t pyr_stride = 0;   // floats per sequence pyramid (padded to 4)
+  void* mem = nullptr;      // one device allocation
+  float *in_left = nullptr, *in_right = nullptr;
+  uint8_t* in_u8 = nullptr;
+  float *cur_img = nullptr, *kf_img = nullptr, *cur_dep = nullptr, *kf_dep = nullptr;
+  DepthWork dw;
+  LmLists lists;
+  LmWork lmw;
+  float* T_init = nullptr;
+  LmResult* res = nullptr;
+  SeqState* state = nullptr;
+  int* promote = nullptr;
+  SeqState* h_state = nullptr;  // pinned
+  int G_lm = 1;
+  int frame_id = 0;
+};
+
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* pose_abs, float* pose_kf,
+                         int* is_keyframe, int* status) {
+  odo_ctx* c = t->c;
+  const int n = t->n;
+  const int first = (t->frame_id == 0) ? 1 : 0;
+  const int64_t in_stride = t->npx;
+  c->err.clear();
+  // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
+  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n);
+  if (!first) {
+    // Solve against the keyframe (:215)
+    if (launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1) != 0)
+      return -1;
+    k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
+    c->launches++;
+  }
+  // ComputeDepth on every frame (:226-229), then DepthPyramid (:252)
+  launch_select(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
+  launch_disparity(c, t->w, t->h, t->dp, t->dw, n);
+  launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
+  launch_depth_pyramid(c, t->dw.dep, t->npx, t->cur_dep, t->pyr_stride, t->g, 0, n);
+  k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
+  // keyframe promotion (:258-265): the new keyframe's pyramids and LM point lists
+  {
+    const int64_t nf = t->g.total;
+    dim3 grid((unsigned)((nf / 4 + 255) / 256 + 1), n);
+    k_promote_copy<<<grid, 256, 0, c->stream>>>(t->cur_img, t->kf_img, t->pyr_stride, t->promote);
+    k_promote_copy<<<grid, 256, 0, c->stream>>>(t->cur_dep, t->kf_dep, t->pyr_stride, t->promote);
+    c->launches += 3;
+  }
+  launch_lm_prepare(c, t->kf_img, t->pyr_stride, t->kf_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote);
+  t->lm.lambda = 0.01f;  // Reset(pose, 0.01f)
+  ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state, t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (!c->err.empty()) return -1;
+  int rc = 0;
+  for (int b = 0; b < n; b++) {
+    const SeqState& s = t->h_state[b];
+    if (pose_abs) std::memcpy(pose_abs + 16 * b, s.cur_pose, sizeof(float) * 16);
+    if (pose_kf) std::memcpy(pose_kf + 16 * b, s.pose_kf, sizeof(float) * 16);
+    if (is_keyframe) is_keyframe[b] = s.promote;
+    if (status) status[b] = s.status;
+    if (s.status != 0) rc = -1;
+  }
+  t->frame_id++;
+  return rc;
+}
+
+extern "C" {
+
+int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const odo_lm_params* lm,
+                       const odo_depth_params* dp, odo_tracker** out) {
+  if (!c || !out || !lm || !dp || n_seq < 1 || levels < 1 || levels > ODO_MAX_LEVELS) return -1;
+  *out = nullptr;
+  if (w - 2 * dp->boundary < 32 || h - 2 * dp->boundary < 16 || dp->boundary < 2 || w > 65535 || h > 32767) {
+    c->err = "tracker: image too small for the 16x32 selection grid";
+    return -1;
+  }
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  odo_tracker* t = new odo_tracker();
+  t->c = c;
+  t->w = w;
+  t->h = h;
+  t->levels = levels;
+  t->n = n_seq;
+  t->g = make_geom(w, h, levels);
+  t->lm = *lm;
+  t->dp = *dp;
+  t->npx = (int64_t)w * h;
+  t->pyr_stride = (t->g.total + 3) / 4 * 4;
+  // CTAs per sequence for the persistent LM kernel: fill the SMs across the batch
+  int G = c->sm_count / n_seq;
+  const int gmax = (int)((t->npx + 4095) / 4096);
+  if (G > gmax) G = gmax;
+  if (G < 1) G = 1;
+  t->G_lm = G;
+  size_t bytes = 0;
+  const size_t in_b = al256(sizeof(float) * t->npx * n_seq);
+  const size_t u8_b = al256((size_t)t->npx * n_seq * 2);
+  const size_t pyr_b = al256(sizeof(float) * t->pyr_stride * n_seq);
+  const size_t dw_b = al256(depth_work_bytes(w, h, n_seq, false));
+  LmLists tmpL;
+  const size_t ll_b = al256(lm_lists_bytes(t->g, n_seq, &tmpL));
+  const size_t lw_b = al256(lm_work_bytes(t->g, n_seq, G));
+  const size_t ti_b = al256(sizeof(float) * 16 * n_seq);
+  const size_t rs_b = al256(sizeof(LmResult) * n_seq);
+  const size_t st_b = al256(sizeof(SeqState) * n_seq);
+  const size_t pf_b = al256(sizeof(int) * n_seq);
+  bytes = in_b * 2 + u8_b + pyr_b * 4 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
+  if (cudaMalloc(&t->mem, bytes) != cudaSuccess) {
+    c->err = "tracker: cudaMalloc failed";
+    delete t;
+    return -1;
+  }
+  cudaMemsetAsync(t->mem, 0, bytes, c->stream);
+  char* p = (char*)t->mem;
+  t->in_left = (float*)p; p += in_b;
+  t->in_right = (float*)p; p += in_b;
+  t->in_u8 = (uint8_t*)p; p += u8_b;
+  t->cur_img = (float*)p; p += pyr_b;
+  t->kf_img = (float*)p; p += pyr_b;
+  t->cur_dep = (float*)p; p += pyr_b;
+  t->kf_dep = (float*)p; p += pyr_b;
+  depth_work_bind(&t->dw, p, w, h, n_seq, false); p += dw_b;
+  lm_lists_bind(&t->lists, p, t->g, n_seq); p += ll_b;
+  lm_work_bind(&t->lmw, p, t->g, n_seq, G); p += lw_b;
+  t->T_init = (float*)p; p += ti_b;
+  t->res = (LmResult*)p; p += rs_b;
+  t->state = (SeqState*)p; p += st_b;
+  t->promote = (int*)p; p += pf_b;
+  if (cudaMallocHost(&t->h_state, sizeof(SeqState) * n_seq) != cudaSuccess) {
+    cudaFree(t->mem);
+    delete t;
+    c->err = "tracker: cudaMallocHost failed";
+    return -1;
+  }
+  k_track_init<<<(n_seq + 63) / 64, 64, 0, c->stream>>>(t->state, t->T_init, n_seq);
+  c->launches++;
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  *out = t;
+  return 0;
+}
+
+void odo_tracker_destroy(odo_tracker* t) {
+  if (!t) return;
+  cudaSetDevice(t->c->device);
+  cudaStreamSynchronize(t->c->stream);
+  cudaFree(t->mem);
+  cudaFreeHost(t->h_state);
+  delete t;
+}
+
+int odo_tracker_step(odo_tracker* t, const float* const* left, const float* const* right, float* pose_abs,
+                     float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || !left || !right) return -1;
+  odo_ctx* c = t->c;
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t bytes = sizeof(float) * t->npx;
+  for (int b = 0; b < t->n; b++) {
+    ODO_CUDA_OK(c, cudaMemcpyAsync(t->in_left + b * t->npx, left[b], bytes, cudaMemcpyHostToDevice, c->stream));
+    ODO_CUDA_OK(c, cudaMemcpyAsync(t->in_right + b * t->npx, right[b], bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  return tracker_frame(t, t->in_left, t->in_right, pose_abs, pose_kf, is_keyframe, status);
+}
+
+int odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right, float* pose_abs,
+                        float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || !left || !right) return -1;
+  odo_ctx* c = t->c;
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  uint8_t* l8 = t->in_u8;
+  uint8_t* r8 = t->in_u8 + t->npx * t->n;
+  for (int b = 0; b < t->n; b++) {
+    ODO_CUDA_OK(c, cudaMemcpyAsync(l8 + b * t->npx, left[b], (size_t)t->npx, cudaMemcpyHostToDevice, c->stream));
+    ODO_CUDA_OK(c, cudaMemcpyAsync(r8 + b * t->npx, right[b], (size_t)t->npx, cudaMemcpyHostToDevice, c->stream));
+  }
+  // gray_8u.convertTo(gray, CV_32F), run_odometry_kitti_offline.cpp:348,358
+  launch_u8_to_f32(c, l8, t->in_left, t->npx * t->n);
+  launch_u8_to_f32(c, r8, t->in_right, t->npx * t->n);
+  return tracker_frame(t, t->in_left, t->in_right, pose_abs, pose_kf, is_keyframe, status);
+}
+
+int odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev, float* pose_abs,
+                         float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || !left_dev || !right_dev) return -1;
+  ODO_CUDA_OK(t->c, cudaSetDevice(t->c->device));
+  return tracker_frame(t, left_dev, right_dev, pose_abs, pose_kf, is_keyframe, status);
+}
+
+// ---- single-call depth entry points (batch = 1 over the same kernels) ------------------------------------
+static void* scratch(odo_ctx* c, int slot, size_t bytes) {
+  if (c->scratch_bytes[slot] >= bytes && c->scratch[slot]) return c->scratch[slot];
+  if (c->scratch[slot]) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->scratch[slot]);
+    c->scratch[slot] = nullptr;
+    c->scratch_bytes[slot] = 0;
+  }
+  if (cudaMalloc(&c->scratch[slot], bytes) != cudaSuccess) {
+    c->err = "cudaMalloc failed";
+    c->scratch[slot] = nullptr;
+    return nullptr;
+  }
+  c->scratch_bytes[slot] = bytes;
+  return c->scratch[slot];
+}
+
+static int depth_setup(odo_ctx* c, int w, int h, const odo_depth_params* p, DepthWork* dw, float** in_l, float** in_r) {
+  if (!c || !p || w < 1 || h < 1) return -1;
+  if (p->boundary < 2 || w - 2 * p->boundary < 32 || h - 2 * p->boundary < 16 || w > 65535 || h > 32767) {
+    c->err = "depth: image too small for the 16x32 selection grid / bad boundary";
+    return -1;
+  }
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t npx = (size_t)w * h;
+  void* m = scratch(c, 10, depth_work_bytes(w, h, 1, true));
+  float* in = (float*)scratch(c, 11, al256(npx * 4) * 2);
+  if (!m || !in) return -1;
+  depth_work_bind(dw, m, w, h, 1, true);
+  *in_l = in;
+  *in_r = (float*)((char*)in + al256(npx * 4));
+  return 0;
+}
+
+int odo_select_pixels(odo_ctx* c, const float* left, const float* right, int w, int h, const odo_depth_params* p,
+                      float* blur_left, float* blur_right, uint8_t* val) {
+  DepthWork dw;
+  float *dl, *dr;
+  if (!left || !right || depth_setup(c, w, h, p, &dw, &dl, &dr) != 0) return -1;
+  const size_t npx = (size_t)w * h;
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_select(c, dl, dr, 0, w, h, *p, dw, 1);
+  if (blur_left) ODO_CUDA_OK(c, cudaMemcpyAsync(blur_left, dw.blurL, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (blur_right) ODO_CUDA_OK(c, cudaMemcpyAsync(blur_right, dw.blurR, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (val) ODO_CUDA_OK(c, cudaMemcpyAsync(val, dw.val, npx, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int odo_disparity_search(odo_ctx* c, const float* blur_left, const float* blur_right, int w, int h,
+                         const odo_depth_params* p, const uint8_t* val, float* disp, float* dep, int32_t* match_x,
+                         float* min_ssd) {
+  DepthWork dw;
+  float *dl, *dr;
+  if (!blur_left || !blur_right || !val || depth_setup(c, w, h, p, &dw, &dl, &dr) != 0) return -1;
+  const size_t npx = (size_t)w * h;
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.blurL, blur_left, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.blurR, blur_right, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.val, val, npx, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemsetAsync(dw.disp, 0, npx * 4, c->stream));
+  ODO_CUDA_OK(c, cudaMemsetAsync(dw.dep, 0, npx * 4, c->stream));
+  ODO_CUDA_OK(c, cudaMemsetAsync(dw.match_x, 0xff, npx * 4, c->stream));
+  ODO_CUDA_OK(c, cudaMemsetAsync(dw.min_ssd, 0, npx * 4, c->stream));
+  ODO_CUDA_OK(c, cudaMemsetAsync(dw.stats, 0, sizeof(odo_depth_stats), c->stream));
+  launch_disparity(c, w, h, *p, dw, 1);
+  if (disp) ODO_CUDA_OK(c, cudaMemcpyAsync(disp, dw.disp, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (dep) ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (match_x) ODO_CUDA_OK(c, cudaMemcpyAsync(match_x, dw.match_x, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (min_ssd) ODO_CUDA_OK(c, cudaMemcpyAsync(min_ssd, dw.min_ssd, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int odo_depth_optimize(odo_ctx* c, const float* left, const float* right, int w, int h, const odo_depth_params* p,
+                       float* dep, uint8_t* val, odo_depth_stats* st) {
+  DepthWork dw;
+  float *dl, *dr;
+  if (!left || !right || !dep || !val || depth_setup(c, w, h, p, &dw, &dl, &dr) != 0) return -1;
+  const size_t npx = (size_t)w * h;
+  // pixel list in raster order from the caller's mask (:106-116); the list kernel capacity is 512*80
+  std::vector<int> list((size_t)dw.cap, -1);
+  int n = 0;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      if (val[(size_t)y * w + x] == 1) {
+        if (n < dw.cap) list[n] = (y << 16) | x;
+        n++;
+      }
+  if (n > dw.cap || n > p->max_residuals) {  // quirk Q7
+    c->err = "depth_optimize: more valid pixels than max_residuals";
+    if (st) { std::memset(st, 0, sizeof(*st)); st->status = -1; }
+    return -1;
+  }
+  odo_depth_stats hs;
+  std::memset(&hs, 0, sizeof(hs));
+  hs.n_selected = n;
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.dep, dep, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.val, val, npx, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.sel_xy, list.data(), sizeof(int) * dw.cap, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));  // list/hs are host temporaries
+  launch_depth_refine(c, dl, dr, 0, w, h, *p, dw, 1);
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(val, dw.val, npx, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(&hs, dw.stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (st) *st = hs;
+  return hs.status;
+}
+
+int odo_compute_depth(odo_ctx* c, const float* left, const float* right, int w, int h, const odo_depth_params* p,
+                      uint8_t* val, float* disp, float* dep, odo_depth_stats* st) {
+  DepthWork dw;
+  float *dl, *dr;
+  if (!left || !right || depth_setup(c, w, h, p, &dw, &dl, &dr) != 0) return -1;
+  const size_t npx = (size_t)w * h;
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  launch_select(c, dl, dr, 0, w, h, *p, dw, 1);
+  launch_disparity(c, w, h, *p, dw, 1);
+  launch_depth_refine(c, dl, dr, 0, w, h, *p, dw, 1);
+  odo_depth_stats hs;
+  if (val) ODO_CUDA_OK(c, cudaMemcpyAsync(val, dw.val, npx, cudaMemcpyDeviceToHost, c->stream));
+  if (disp) ODO_CUDA_OK(c, cudaMemcpyAsync(disp, dw.disp, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (dep) ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(&hs, dw.stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (st) *st = hs;
+  if (hs.status != 0) c->err = "Depth optimization failed!";
+  return hs.status;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+"""Synthetic KITTI-shaped stereo data: the analytic "street corridor" of SURVEY.md section 8(d).
+
+Textured ground plane y = +1.65 m (camera y points down), two side walls x = +-6 m and an optional
+end wall, rendered per frame by ray/plane intersection (exact per-pixel depth) with a procedural
+texture  tex(a,b) = 127.5 + sum_k A_k cos(2 pi f_k.(a,b) + phi_k)  (wavelengths 0.05 .. 2 m,
+analytically pre-filtered by the pixel footprint so distant texture fades instead of aliasing),
+quantised to u8 -- exactly how the reference ingests frames (imread GRAYSCALE -> convertTo CV_32F,
+run_odometry_kitti_offline.cpp:334-359).  Camera constants are the ones hard-coded in the reference
+hot path (fx = fy = 718.856, cx = 607.1928, cy = 185.2157, baseline = 386.1448/718.856 m).
+
+This is data plumbing for tests and bench.py (torch tensors on CPU or GPU); it is not part of the
+hot path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+FX = 718.856
+CX = 607.1928
+CY = 185.2157
+BASELINE = 386.1448 / 718.856
+BASE_SEED = 20190113
+N_COS = 48
+
+
+@dataclass
+class Scene:
+    seed: int
+    ground_y: float = 1.65
+    wall_x: float = 6.0
+    end_wall_z: float = 60.0        # world z of the end wall (math.inf disables it)
+    contrast: float = 38.0          # RMS of the texture in grey levels
+
+    def __post_init__(self):
+        rng = np.random.default_rng(self.seed)
+        # four surfaces: ground, left wall, right wall, end wall
+        lam = np.exp(rng.uniform(np.log(0.05), np.log(2.0), size=(4, N_COS)))
+        ang = rng.uniform(0, 2 * np.pi, size=(4, N_COS))
+        self.fa = (np.cos(ang) / lam).astype(np.float64)
+        self.fb = (np.sin(ang) / lam).astype(np.float64)
+        self.phi = rng.uniform(0, 2 * np.pi, size=(4, N_COS))
+        amp = rng.uniform(0.5, 1.0, size=(4, N_COS)) * np.sqrt(lam)   # more energy at long wavelengths
+        amp *= self.contrast / np.sqrt(0.5 * (amp ** 2).sum(axis=1, keepdims=True))
+        self.amp = amp
+
+
+def pose_from_motion(tx=0.0, ty=0.0, tz=0.0, rx=0.0, ry=0.0, rz=0.0):
+    """Camera-to-world 4x4 (float64): rotation Rz(rz) Ry(ry) Rx(rx) (radians), translation (tx,ty,tz)."""
+    cx_, sx = math.cos(rx), math.sin(rx)
+    cy_, sy = math.cos(ry), math.sin(ry)
+    cz, sz = math.cos(rz), math.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx_, -sx], [0, sx, cx_]])
+    Ry = np.array([[cy_, 0, sy], [0, 1, 0], [-sy, 0, cy_]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = (tx, ty, tz)
+    return T
+
+
+def trajectory(n_frames: int, step=0.8, yaw_amp_deg=0.4, period=100.0):
+    """Config-3 trajectory: `step` m/frame forward, yaw = yaw_amp * sin(2 pi t / period)."""
+    poses = []
+    z = 0.0
+    x = 0.0
+    for t in range(n_frames):
+        yaw = math.radians(yaw_amp_deg) * math.sin(2 * math.pi * t / period)
+        poses.append(pose_from_motion(tx=x, tz=z, ry=yaw))
+        x += step * math.sin(yaw)
+        z += step * math.cos(yaw)
+    return poses
+
+
+def relative_pose(T_wc1, T_wc2):
+    """The T the LM estimates: p2 = T p1 (frame-1 camera coordinates -> frame-2)."""
+    return np.linalg.inv(T_wc2) @ T_wc1
+
+
+def _texture(scene: Scene, s: int, a, b, sig_a, sig_b):
+    """sum_k A_k exp(-2 pi^2 (sig_a^2 fa^2 + sig_b^2 fb^2)) cos(2 pi (fa a + fb b) + phi)"""
+    dev = a.device
+    fa = torch.as_tensor(scene.fa[s], device=dev, dtype=torch.float64)
+    fb = torch.as_tensor(scene.fb[s], device=dev, dtype=torch.float64)
+    phi = torch.as_tensor(scene.phi[s], device=dev, dtype=torch.float64)
+    amp = torch.as_tensor(scene.amp[s], device=dev, dtype=torch.float64)
+    out = torch.zeros_like(a)
+    # chunk over cosines to bound memory
+    for k0 in range(0, N_COS, 8):
+        sl = slice(k0, k0 + 8)
+        arg = 2 * math.pi * (a[..., None] * fa[sl] + b[..., None] * fb[sl]) + phi[sl]
+        att = torch.exp(-2 * math.pi ** 2 * (sig_a[..., None] ** 2 * fa[sl] ** 2 + sig_b[..., None] ** 2 * fb[sl] ** 2))
+        out += (amp[sl] * att * torch.cos(arg)).sum(-1)
+    return out
+
+
+def render(scene: Scene, T_wc, w=1241, h=376, device="cpu", fx=FX, cx=CX, cy=CY):
+    """Render one view. Returns (u8 image [h,w] torch.uint8, z-depth [h,w] float64) on `device`."""
+    dev = torch.device(device)
+    T = torch.as_tensor(np.asarray(T_wc), dtype=torch.float64, device=dev)
+    R, c = T[:3, :3], T[:3, 3]
+    v, u = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float64),
+                          torch.arange(w, device=dev, dtype=torch.float64), indexing="ij")
+    dc = torch.stack([(u - cx) / fx, (v - cy) / fx, torch.ones_like(u)], -1)   # fy == fx (quirk Q3)
+    dw = dc @ R.T
+    inf = torch.full_like(u, float("inf"))
+    # ray parameter t (== camera z-depth since dc.z == 1) for each surface
+    tg = torch.where(dw[..., 1] > 1e-9, (scene.ground_y - c[1]) / dw[..., 1], inf)
+    tl = torch.where(dw[..., 0] < -1e-9, (-scene.wall_x - c[0]) / dw[..., 0], inf)
+    tr = torch.where(dw[..., 0] > 1e-9, (scene.wall_x - c[0]) / dw[..., 0], inf)
+    if math.isfinite(scene.end_wall_z):
+        te = torch.where(dw[..., 2] > 1e-9, (scene.end_wall_z - c[2]) / dw[..., 2], inf)
+    else:
+        te = inf
+    ts = torch.stack([tg, tl, tr, te], 0)
+    ts = torch.where(ts > 0, ts, inf)
+    t, which = ts.min(0)
+    t = torch.clamp(t, max=1e4)
+    P = c + dw * t[..., None]
+    foot = t / fx                                    # isotropic pixel footprint at range t [m]
+    img = torch.full_like(u, 127.5)
+    for s in range(4):
+        m = which == s
+        if not bool(m.any()):
+            continue
+        if s == 0:      # ground: (X, Z); Z stretches by t / height at grazing incidence
+            a, b = P[..., 0], P[..., 2]
+            hgt = torch.clamp(scene.ground_y - c[1], min=0.05)
+            sa, sb = 0.5 * foot, 0.5 * foot * torch.clamp(t / hgt, min=1.0)
+        elif s in (1, 2):  # walls: (Y, Z)
+            a, b = P[..., 1], P[..., 2]
+            dist = torch.clamp(torch.abs((scene.wall_x if s == 2 else -scene.wall_x) - c[0]), min=0.05)
+            sa, sb = 0.5 * foot, 0.5 * foot * torch.clamp(t / dist, min=1.0)
+        else:           # end wall: (X, Y)
+            a, b = P[..., 0], P[..., 1]
+            sa, sb = 0.5 * foot, 0.5 * foot
+        tex = _texture(scene, s, a[m], b[m], sa[m], sb[m])
+        img[m] = 127.5 + tex
+    img8 = torch.clamp(torch.round(img), 0, 255).to(torch.uint8)
+    return img8, t
+
+
+def right_pose(T_wc, baseline=BASELINE):
+    """Right camera of the rectified rig: centre shifted by +baseline along the camera x axis."""
+    T = np.array(T_wc, dtype=np.float64, copy=True)
+    T[:3, 3] = T[:3, 3] + T[:3, :3] @ np.array([baseline, 0.0, 0.0])
+    return T
+
+
+def render_stereo(scene: Scene, T_wc, w=1241, h=376, device="cpu"):
+    """(left u8, right u8, left z-depth) torch tensors on `device`."""
+    L, z = render(scene, T_wc, w, h, device)
+    R, _ = render(scene, right_pose(T_wc), w, h, device)
+    return L, R, z
+
+
+def make_scene(sequence_id: int = 0, n_frames: int = 1, step=0.8) -> Scene:
+    """Scene for `sequence_id` (seed 20190113 + id) whose end wall stays ahead of the whole trajectory."""
+    return Scene(seed=BASE_SEED + sequence_id, end_wall_z=60.0 + step * max(n_frames - 1, 0))

@@ -1,0 +1,104 @@
+"""K3/K4/K5 parity: selection mask and integer disparities bit-exact, refinement vs oracle. Needs a GPU."""
+import numpy as np
+import pytest
+
+import oracle
+from odometry_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def bits_equal(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def pairs(synth_data):
+    out = []
+    for sid in (0, 3):
+        d = synth_data.pair(sid)
+        out.append((d["L1"], d["R1"]))
+    rng = np.random.default_rng(2)
+    # a hard case: pure noise right image (many failed matches, ties impossible but thresholds bite)
+    out.append((out[0][0], rng.integers(0, 256, out[0][0].shape).astype(np.float32)))
+    # a flat case: constant images => zero gradients everywhere, nothing selected
+    out.append((np.full((376, 1241), 90, np.float32), np.full((376, 1241), 90, np.float32)))
+    return out
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_selection_mask_bit_exact(ctx, pairs, i):
+    L, R = pairs[i]
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    rc, bl, br, val = ctx.select_pixels(L, R, dp)
+    orc, obl, obr, oval = oracle.select_pixels(L, R, op)
+    assert rc == 0 and orc == 0
+    assert bits_equal(bl, obl) and bits_equal(br, obr)
+    assert np.array_equal(val, oval)
+    assert val.reshape(-1).sum() <= 512 * 80
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_disparity_indices_bit_exact(ctx, pairs, i):
+    L, R = pairs[i]
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    _, obl, obr, oval = oracle.select_pixels(L, R, op)
+    orc, odisp, odep, omatch, ossd = oracle.disparity_search(obl, obr, oval, op)
+    rc, disp, dep, match, ssd = ctx.disparity_search(obl, obr, oval, dp)
+    assert rc == 0 and orc == 0
+    assert np.array_equal(match, omatch)            # integer argmin, first-minimum tie rule
+    assert bits_equal(disp, odisp) and bits_equal(dep, odep)
+    sel = oval == 1
+    assert bits_equal(ssd[sel], ossd[sel])          # the 8-tap SSD in the AVX tree order
+
+
+def test_disparity_tie_break_first_minimum(ctx):
+    """Periodic right image => many exactly equal SSD minima; the smallest column must win."""
+    h, w = 376, 1241
+    x = np.arange(w)
+    row = ((x % 16) * 13 % 97).astype(np.float32)
+    R = np.tile(row, (h, 1))
+    L = np.roll(R, 5, axis=1)
+    dp, op = capi.default_depth_params(ssd_th=1e9), oracle.depth_params(ssd_th=1e9)
+    val = np.zeros((h, w), np.uint8)
+    val[10:360:7, 40:1200:11] = 1
+    orc, odisp, odep, omatch, ossd = oracle.disparity_search(L, R, val, op)
+    rc, disp, dep, match, ssd = ctx.disparity_search(L, R, val, dp)
+    assert np.array_equal(match, omatch) and bits_equal(disp, odisp)
+    assert (omatch[val == 1] < 40).mean() > 0.9     # the period makes early columns win
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_refinement_matches_oracle(ctx, pairs, i):
+    L, R = pairs[i]
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    _, obl, obr, oval = oracle.select_pixels(L, R, op)
+    _, odisp, odep, _, _ = oracle.disparity_search(obl, obr, oval, op)
+    orc, rdep, rval, ost = oracle.depth_optimize(L, R, odep, oval, op)
+    rc, gdep, gval, gst = ctx.depth_optimize(L, R, odep, oval, dp)
+    assert rc == orc == 0
+    assert gst.iters == ost.iters
+    assert np.array_equal(gval, rval)
+    assert gst.n_valid == ost.n_valid == int(rval.sum())
+    assert np.allclose(gdep, rdep, rtol=1e-6, atol=1e-9)
+    assert gst.cost == pytest.approx(ost.cost, rel=1e-6)
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_compute_depth_end_to_end(ctx, pairs, i):
+    L, R = pairs[i]
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    orc, oval, odisp, odep, ost = oracle.compute_depth(L, R, op)
+    rc, val, disp, dep, st = ctx.compute_depth(L, R, dp)
+    assert rc == orc
+    assert st.n_selected == ost.n_selected
+    assert bits_equal(disp, odisp)
+    assert np.array_equal(val, oval)
+    assert np.allclose(dep, odep, rtol=1e-6, atol=1e-9)
+    assert (st.iters, st.n_valid) == (ost.iters, ost.n_valid)
+
+
+def test_compute_depth_rejects_tiny_images(ctx):
+    dp = capi.default_depth_params()
+    rc, *_ = ctx.compute_depth(np.zeros((20, 30), np.float32), np.zeros((20, 30), np.float32), dp)
+    assert rc == -1
