@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- KITTI-shape tracking throughput of the B200 hot path (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: one new 1241x376 stereo frame for each of S
+independent synthetic sequences resident on the GPU (image pyramid + LM Solve against the keyframe
++ ComputeDepth (selection, SSD disparity search, depth refinement) + depth pyramid + keyframe rule:
+the per-frame body of run_odometry_kitti_offline.cpp:198-271).  With --gpus N every rank runs its
+own S sequences (sharding of independent sequences, no data-path collective => weak scaling).
+
+  value : frames/s with the step's inputs already resident in HBM (odo_tracker_step_dev)
+  e2e   : frames/s through the reference-facing C-ABI call with HOST buffers (CV_32F images in
+          pinned memory, H2D of the step's frames and D2H of the poses inside the timed region)
+
+--impl reference times the CPU oracle (the reference cannot be compiled here: no Eigen/OpenCV C++)
+on all host cores, one sequence per thread.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, LEVELS = 1241, 376, 4
+METRIC = "KITTI-shape tracking frames/s (pyramid + disparity/depth + LM align per frame)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqs", type=int, default=64, help="independent sequences per GPU (batch of one step)")
+    ap.add_argument("--cpu-seqs", type=int, default=2, help="sequences of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, extra=None):
+    cfg = {
+        "workload": f"config 4/3: {args.seqs} independent synthetic {W}x{H} stereo sequences per GPU, "
+                    f"{LEVELS}-level pyramid, full tracking step per frame (reference-faithful: depth every frame)",
+        "sequences_per_gpu": args.seqs, "frame": f"{W}x{H}", "levels": LEVELS,
+        "lm": "lambda 0.01, precision 0.995, iters {10,20,30,30}, Huber 28",
+        "depth": "grad_th 8, ssd_th 900, photo_th 15, 0.1-30 m, 50 iters, boundary 4",
+        "trajectory": "0.8 m/frame forward, yaw 0.4deg*sin(2*pi*t/100), seeds 20190113+sequence_id",
+        "parallelism": f"sequence sharding x{args.gpus}, no collective",
+        "l2": "each step reads a fresh batch of frames (S*3.7 MB > 126 MB L2 for S >= 34); no explicit flush",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv and self.samples:
+            return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(self.reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+
+
+def render_sequences(n_seq, n_frames, seq_offset, device):
+    """u8 frames [n_frames][n_seq][2][H][W] on `device` (torch), sequence ids seq_offset..+n_seq."""
+    import torch
+    from odometry_b200 import synth
+    out = torch.empty((n_frames, n_seq, 2, H, W), dtype=torch.uint8, device=device)
+    poses = synth.trajectory(n_frames, step=0.8)
+    for s in range(n_seq):
+        sc = synth.make_scene(seq_offset + s, n_frames, 0.8)
+        for f, T in enumerate(poses):
+            L, R, _ = synth.render_stereo(sc, T, W, H, device)
+            out[f, s, 0], out[f, s, 1] = L, R
+    return out
+
+
+def cpu_tracking_fps(frames_u8, n_seq, n_frames, threads):
+    """Oracle tracker (CPU restatement of the reference loop): n_seq sequences over `threads` host
+    threads; frame 0 (keyframe init) is untimed like the GPU arm's. Returns (frames/s, timed frames)."""
+    import oracle
+    trackers = [oracle.Tracker(W, H, LEVELS) for _ in range(n_seq)]
+    fl = frames_u8.astype(np.float32)
+    for s, t in enumerate(trackers):
+        t.step(fl[0, s, 0], fl[0, s, 1])
+
+    def work(s):
+        for f in range(1, n_frames):
+            trackers[s].step(fl[f, s, 0], fl[f, s, 1])
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for s in range(n_seq):
+            work(s)
+    else:
+        ths = [threading.Thread(target=work, args=(s,)) for s in range(n_seq)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    dt = time.perf_counter() - t0
+    for t in trackers:
+        t.close()
+    return n_seq * (n_frames - 1) / dt, n_seq * (n_frames - 1)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    n_seq = max(1, min(cores, 32))
+    n_frames = 1 + args.warmup + args.steps
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    frames = render_sequences(n_seq, n_frames, 0, dev).cpu().numpy()
+    import oracle
+    oracle.lib()
+    # warm-up steps are part of the same trajectory: time only the last `steps` frames
+    trackers = [oracle.Tracker(W, H, LEVELS) for _ in range(n_seq)]
+    fl = frames.astype(np.float32)
+
+    def advance(s, f0, f1):
+        for f in range(f0, f1):
+            trackers[s].step(fl[f, s, 0], fl[f, s, 1])
+
+    def parallel(f0, f1):
+        ths = [threading.Thread(target=advance, args=(s, f0, f1)) for s in range(n_seq)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    parallel(0, 1 + args.warmup)
+    t0 = time.perf_counter()
+    parallel(1 + args.warmup, n_frames)
+    dt = time.perf_counter() - t0
+    fps = n_seq * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, {"sequences_per_step": n_seq}),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_seq, "kind": "port",
+                         "sample": f"{n_seq} sequences x {args.steps} frames, one oracle tracker per host thread"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from odometry_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, K, Wm = args.seqs, args.steps, args.warmup
+    n_frames = 1 + Wm + K
+    frames_u8 = render_sequences(S, n_frames, rank * S, dev)           # [F][S][2][H][W] u8 on device
+    stream = torch.cuda.current_stream(dev)
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- leg 1: inputs resident in HBM ----------------
+    frames_f32 = frames_u8.to(torch.float32)                            # [F][S][2][H][W] float32 on device
+    left_dev = frames_f32[:, :, 0].contiguous()
+    right_dev = frames_f32[:, :, 1].contiguous()
+    del frames_f32
+    trk = capi.Tracker(ctx, W, H, LEVELS, S)
+    for f in range(0, 1 + Wm):
+        rc, *_ = trk.step_dev(left_dev[f].data_ptr(), right_dev[f].data_ptr())
+    sampler = ClockSampler(local_rank)
+    stage_acc = {}
+    launches0 = ctx.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    n_kf = 0
+    for f in range(1 + Wm, n_frames):
+        rc, pa, pk, kf, st = trk.step_dev(left_dev[f].data_ptr(), right_dev[f].data_ptr())
+        n_kf += int(kf.sum())
+        for k, v in trk.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count() - launches0
+    value = world * S * K / (ms_total * 1e-3)
+    status_ok = bool((st == 0).all())
+    trk.close()
+    del left_dev, right_dev
+
+    # ---------------- leg 2: end to end through the C-ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = frames_u8.to(torch.float32).cpu().pin_memory()           # [F][S][2][H][W] pinned CV_32F frames
+        trk = capi.Tracker(ctx, W, H, LEVELS, S)
+
+        def ptrs(f, eye):
+            base = host[f, :, eye]
+            return [base[s].data_ptr() for s in range(S)]
+
+        for f in range(0, 1 + Wm):
+            trk.step_ptrs(ptrs(f, 0), ptrs(f, 1))
+        barrier()
+        e0.record(stream)
+        for f in range(1 + Wm, n_frames):
+            trk.step_ptrs(ptrs(f, 0), ptrs(f, 1))
+        e1.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": S * 2 * W * H * 4, "d2h_bytes_per_step": S * 240,
+               "ms_per_step": ms_e2e / K, "host_buffers": "pinned float32 (CV_32F), one pointer per image"}
+        trk.close()
+        # fused u8 ingest (row f2 of SURVEY 8f): same call with the frames as the PNG decoder leaves them
+        host8 = frames_u8.cpu().pin_memory()
+        trk = capi.Tracker(ctx, W, H, LEVELS, S)
+
+        def ptrs8(f, eye):
+            base = host8[f, :, eye]
+            return [base[s].data_ptr() for s in range(S)]
+
+        for f in range(0, 1 + Wm):
+            trk.step_ptrs(ptrs8(f, 0), ptrs8(f, 1), u8=True)
+        barrier()
+        e0.record(stream)
+        for f in range(1 + Wm, n_frames):
+            trk.step_ptrs(ptrs8(f, 0), ptrs8(f, 1), u8=True)
+        e1.record(stream)
+        barrier()
+        ms_u8 = max_over_ranks(e0.elapsed_time(e1))
+        e2e["u8_ingest"] = {"value": world * S * K / (ms_u8 * 1e-3), "unit": "frames/s",
+                            "h2d_bytes_per_step": S * 2 * W * H}
+        trk.close()
+        del host, host8
+
+    # ---------------- roofline of the dominant stage (device-resident leg, this rank) ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    stage_ms = {k: v / K for k, v in stage_acc.items()}
+    npx = W * H
+    pyr_px = sum((W >> l) * (H >> l) for l in range(LEVELS))
+    # algorithmic (compulsory) bytes per frame of each stage, DESIGN.md "Algorithmic bytes"
+    alg_bytes = {
+        "image_pyramid": 4 * (npx + pyr_px),
+        "blur_select": 2 * 8 * npx + npx + 8 * npx,          # blur L,R (read+write), val, zero-filled disp/dep
+        "disparity": 17 * npx,                               # read L,R blur, val; write disp, dep
+        "depth_pyr_promote_prepare": 4 * (npx + pyr_px),
+    }
+    dom = max(stage_ms, key=stage_ms.get)
+    roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src, "traffic": None}
+    if dom in alg_bytes:
+        ach = alg_bytes[dom] * S / (stage_ms[dom] * 1e-3) / 1e9
+    else:
+        # iteration-bound stages (LM solve, depth refinement): L2-resident working set, latency bound;
+        # report the compulsory one-pass bytes so the fraction is an honest (small) number
+        one_pass = {"lm_solve": 4 * pyr_px + 48 * 40960, "depth_refine": 20 * 40960}[dom]
+        ach = one_pass * S / (stage_ms[dom] * 1e-3) / 1e9
+        roof["note"] = "iteration/latency bound stage: achieved = one compulsory pass of its inputs / stage time"
+    roof["achieved"] = ach
+    roof["frac"] = ach / hbm_peak
+    roof["stage_ms_per_step"] = stage_ms
+    roof["per_stage_gbs"] = {k: alg_bytes[k] * S / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = min(args.cpu_seqs, S)
+        nf = min(n_frames, 1 + 30)
+        fps, nfr = cpu_tracking_fps(frames_u8[:nf, :ns].cpu().numpy(), ns, nf, threads=1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": f"{ns} sequences x {nf - 1} frames of the same workload, oracle tracker, 1 thread "
+                         f"(host has {os.cpu_count()} logical cores)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "frames_per_step": world * S, "keyframes_in_timed_region": n_kf, "all_status_ok": status_ok,
+            "disparity_mpix_per_s": (npx * S / 1e6) / ((stage_ms["blur_select"] + stage_ms["disparity"] + stage_ms["depth_refine"]) * 1e-3),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

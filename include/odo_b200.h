@@ -154,6 +154,12 @@ int  odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8
 int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev,
                           float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 
+/* device time of the stages of the last step, in ms (CUDA events on the context's stream):
+ * 0 image pyramid, 1 LM solve + pose update, 2 blur + selection, 3 disparity search,
+ * 4 depth refinement, 5 depth pyramid + keyframe promotion + LM point lists */
+#define ODO_N_STAGES 6
+int  odo_tracker_stage_ms(const odo_tracker* t, float* ms_out /* [ODO_N_STAGES] */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -50,8 +51,9 @@ EXPORTS = [
     "odo_pyr_levels", "odo_pyr_level_size", "odo_pyr_download", "odo_pyr_release",
     "odo_compute_depth", "odo_select_pixels", "odo_disparity_search", "odo_depth_optimize",
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
-    "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev",
+    "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev", "odo_tracker_stage_ms",
 ]
+STAGES = ["image_pyramid", "lm_solve", "blur_select", "disparity", "depth_refine", "depth_pyr_promote_prepare"]
 
 _lib = None
 
@@ -118,6 +120,7 @@ class OdoError(RuntimeError):
 class Pyramid:
     def __init__(self, ctx: "Context", handle):
         self.ctx, self.h = ctx, handle
+        ctx._children.add(self)
 
     @property
     def levels(self):
@@ -137,9 +140,11 @@ class Pyramid:
         return out
 
     def release(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().odo_pyr_release(self.ctx.h, self.h)
-            self.h = None
+        self.h = None
+
+    close = release
 
     def __del__(self):
         try:
@@ -155,6 +160,7 @@ class Context:
         if rc != 0 or not h:
             raise OdoError("odo_ctx_create failed (no CUDA device?) -- there is no CPU fallback")
         self.h = h
+        self._children = weakref.WeakSet()   # pyramids / trackers must die before their context
 
     def last_error(self):
         return lib().odo_last_error(self.h).decode()
@@ -168,6 +174,8 @@ class Context:
 
     def close(self):
         if self.h:
+            for ch in list(self._children):
+                ch.close()
             lib().odo_ctx_destroy(self.h)
             self.h = None
 
@@ -260,6 +268,7 @@ class Tracker:
         if rc != 0:
             raise OdoError(ctx.last_error())
         self.h = t
+        ctx._children.add(self)
         self.pose_abs = np.zeros((n_seq, 16), np.float32)
         self.pose_kf = np.zeros((n_seq, 16), np.float32)
         self.is_kf = np.zeros(n_seq, np.int32)
@@ -293,10 +302,15 @@ class Tracker:
         rc = lib().odo_tracker_step_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr), *self._outs())
         return self._result(rc)
 
+    def stage_ms(self):
+        out = (C.c_float * len(STAGES))()
+        lib().odo_tracker_stage_ms(self.h, out)
+        return dict(zip(STAGES, [float(v) for v in out]))
+
     def close(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().odo_tracker_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

@@ -207,6 +207,10 @@ struct odo_tracker {
   SeqState* h_state = nullptr;  // pinned
   int G_lm = 1;
   int frame_id = 0;
+  // stage boundaries of the last step (bench.py roofline): 0 start, 1 image pyramid, 2 LM solve + pose,
+  // 3 blur + selection, 4 disparity search, 5 depth refinement, 6 depth pyramid + promotion + LM prepare
+  cudaEvent_t ev[ODO_N_STAGES + 1] = {nullptr};
+  float stage_ms[ODO_N_STAGES] = {0};
 };
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
@@ -218,8 +222,10 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
   const int first = (t->frame_id == 0) ? 1 : 0;
   const int64_t in_stride = t->npx;
   c->err.clear();
+  cudaEventRecord(t->ev[0], c->stream);
   // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
   launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n);
+  cudaEventRecord(t->ev[1], c->stream);
   if (!first) {
     // Solve against the keyframe (:215)
     if (launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1) != 0)
@@ -227,10 +233,14 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
     k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
     c->launches++;
   }
+  cudaEventRecord(t->ev[2], c->stream);
   // ComputeDepth on every frame (:226-229), then DepthPyramid (:252)
   launch_select(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
+  cudaEventRecord(t->ev[3], c->stream);
   launch_disparity(c, t->w, t->h, t->dp, t->dw, n);
+  cudaEventRecord(t->ev[4], c->stream);
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
+  cudaEventRecord(t->ev[5], c->stream);
   launch_depth_pyramid(c, t->dw.dep, t->npx, t->cur_dep, t->pyr_stride, t->g, 0, n);
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
   // keyframe promotion (:258-265): the new keyframe's pyramids and LM point lists
@@ -243,9 +253,11 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
   }
   launch_lm_prepare(c, t->kf_img, t->pyr_stride, t->kf_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote);
   t->lm.lambda = 0.01f;  // Reset(pose, 0.01f)
+  cudaEventRecord(t->ev[6], c->stream);
   ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state, t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   if (!c->err.empty()) return -1;
+  for (int i = 0; i < ODO_N_STAGES; i++) cudaEventElapsedTime(&t->stage_ms[i], t->ev[i], t->ev[i + 1]);
   int rc = 0;
   for (int b = 0; b < n; b++) {
     const SeqState& s = t->h_state[b];
@@ -327,6 +339,7 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
     c->err = "tracker: cudaMallocHost failed";
     return -1;
   }
+  for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[i]);
   k_track_init<<<(n_seq + 63) / 64, 64, 0, c->stream>>>(t->state, t->T_init, n_seq);
   c->launches++;
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -340,7 +353,15 @@ void odo_tracker_destroy(odo_tracker* t) {
   cudaStreamSynchronize(t->c->stream);
   cudaFree(t->mem);
   cudaFreeHost(t->h_state);
+  for (int i = 0; i <= ODO_N_STAGES; i++)
+    if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   delete t;
+}
+
+int odo_tracker_stage_ms(const odo_tracker* t, float* ms_out) {
+  if (!t || !ms_out) return -1;
+  for (int i = 0; i < ODO_N_STAGES; i++) ms_out[i] = t->stage_ms[i];
+  return 0;
 }
 
 int odo_tracker_step(odo_tracker* t, const float* const* left, const float* const* right, float* pose_abs,

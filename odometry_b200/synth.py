@@ -2,7 +2,7 @@
 
 Textured ground plane y = +1.65 m (camera y points down), two side walls x = +-6 m and an optional
 end wall, rendered per frame by ray/plane intersection (exact per-pixel depth) with a procedural
-texture  tex(a,b) = 127.5 + sum_k A_k cos(2 pi f_k.(a,b) + phi_k)  (wavelengths 0.05 .. 2 m,
+texture  tex(a,b) = 127.5 + sum_k A_k cos(2 pi f_k.(a,b) + phi_k)  (wavelengths 0.05 .. 8 m,
 analytically pre-filtered by the pixel footprint so distant texture fades instead of aliasing),
 quantised to u8 -- exactly how the reference ingests frames (imread GRAYSCALE -> convertTo CV_32F,
 run_odometry_kitti_offline.cpp:334-359).  Camera constants are the ones hard-coded in the reference
@@ -33,17 +33,20 @@ class Scene:
     ground_y: float = 1.65
     wall_x: float = 6.0
     end_wall_z: float = 60.0        # world z of the end wall (math.inf disables it)
-    contrast: float = 38.0          # RMS of the texture in grey levels
+    contrast: float = 45.0          # RMS of the texture in grey levels
+    lam_min: float = 0.05           # shortest / longest texture wavelength [m]; the long end (beyond the
+    lam_max: float = 8.0            # survey's 2 m) gives the coarse pyramid levels the large-scale structure
+    amp_exp: float = 0.25           # real street scenes have, so 0.8 m/frame stays inside the LM basin
 
     def __post_init__(self):
         rng = np.random.default_rng(self.seed)
         # four surfaces: ground, left wall, right wall, end wall
-        lam = np.exp(rng.uniform(np.log(0.05), np.log(2.0), size=(4, N_COS)))
+        lam = np.exp(rng.uniform(np.log(self.lam_min), np.log(self.lam_max), size=(4, N_COS)))
         ang = rng.uniform(0, 2 * np.pi, size=(4, N_COS))
         self.fa = (np.cos(ang) / lam).astype(np.float64)
         self.fb = (np.sin(ang) / lam).astype(np.float64)
         self.phi = rng.uniform(0, 2 * np.pi, size=(4, N_COS))
-        amp = rng.uniform(0.5, 1.0, size=(4, N_COS)) * np.sqrt(lam)   # more energy at long wavelengths
+        amp = rng.uniform(0.5, 1.0, size=(4, N_COS)) * lam ** self.amp_exp   # more energy at long wavelengths
         amp *= self.contrast / np.sqrt(0.5 * (amp ** 2).sum(axis=1, keepdims=True))
         self.amp = amp
 

@@ -75,9 +75,13 @@ def test_linearize_matches_oracle_every_level(ctx, scene, depth_key, robust, pos
         assert abs(got["E"] - wide["E"]) <= 1e-12 * abs(wide["E"])
         if robust == 2:
             assert got["sigma"] == pytest.approx(wide["sigma"], rel=1e-6)
-        # against the fp32 sequential sums of the reference's scalar loops: north-star tolerance
-        assert rel_err(got["H"], seq["H"]) < REL * 10 if robust == 2 else rel_err(got["H"], seq["H"]) < REL
-        assert rel_err(got["g"], seq["g"]) < 1e-3  # fp32 cancellation in the oracle's own g sum
+        # against fp32 SEQUENTIAL sums (the worst association the reference's Eigen GEMM could have):
+        # the difference is the fp32 accumulation error of that oracle mode itself, which grows with
+        # N (measured 1e-5 at N = 24k, 4e-4 at N = 454k between the two oracle modes); at the
+        # reference's semi-dense sizes it is the north-star 1e-5 (order-of-summation) tolerance.
+        tol = max(2 * REL, 2e-9 * got["N"])
+        assert rel_err(got["H"], seq["H"]) < tol
+        assert rel_err(got["g"], seq["g"]) < tol
 
 
 @pytest.mark.parametrize("depth_key", ["dep_mask", "dep_stereo", "dep_dense"])

@@ -39,11 +39,14 @@ def test_tracker_matches_oracle_over_keyframes(ctx, synth_data):
         for got, ref in ((pa[0], opa), (pk[0], opk)):
             ang, tr = pose_err(got, ref)
             assert ang < 1e-4 and tr < 1e-4, f"frame {k}: {ang} {tr}"
-    assert n_kf >= 2      # 0.8 m/frame crosses the 1.1 motion threshold every ~5 frames
-    # sanity against the rendered trajectory
-    gt = np.linalg.inv(seq["poses"][0]) @ seq["poses"][-1]
-    ang, tr = pose_err(pa[0], gt.astype(np.float32))
-    assert tr < 0.35 and ang < 0.02
+        if k == 4:
+            # sanity against the rendered trajectory while still on the first keyframe (after the
+            # first switch the reference's warm start with the pose to the OLD keyframe, quirk A.8,
+            # throws the LM out of its basin on this scene -- replicated)
+            gt = np.linalg.inv(seq["poses"][0]) @ seq["poses"][4]
+            ang, tr = pose_err(pa[0], gt.astype(np.float32))
+            assert tr < 0.05 and ang < 0.01
+    assert n_kf >= 2      # 0.8 m/frame crosses the 1.1 motion threshold at frame 5
     trk.close()
 
 
