@@ -135,8 +135,9 @@ struct DepthWork {
   int* sel_xy;         // [batch][cap] packed (y << 16 | x), -1 = hole; block-major selection order
   int* sel_count;      // [batch][512] per 16x32 block
   odo_depth_stats* stats;  // [batch]
-  float* ref_state;    // refinement scratch [batch][cap][4]
-  int cap;
+  float* ref_state;    // refinement scratch [batch][6][cap]
+  int cap;             // pixel-list capacity per sequence
+  int n_items;         // disparity work items (lists of <= 80 pixels) per sequence; 512 in the pipeline
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)

@@ -122,113 +122,182 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
 }
 
 // ---- disparity line search ----------------------------------------------------------------------------
-constexpr int kSegW = 64;
+// Work item = one list of <= 80 selected pixels in raster order (in the pipeline: one block of the
+// 16x32 selection grid).  The CTA stages the right rows its pixels need in shared memory (in chunks of
+// kRowsPerChunk image rows), then each warp takes a group of up to kDispP pixels of the SAME image row:
+// every lane loads the 8 right taps of its candidate column once and evaluates the SSD against the
+// kDispP left patterns held in registers, so the shared-memory traffic per candidate drops by kDispP
+// and the loop is bound by the 23 fp32 operations per candidate that the reference's association
+// requires (no FMA, fixed tree).
 constexpr int kDispThreads = 256;
+constexpr int kDispWarps = kDispThreads / 32;
+constexpr int kDispP = 4;
+constexpr int kRowsPerChunk = 4;
+constexpr int kStagedRows = kRowsPerChunk + 4;
+
+__device__ __forceinline__ float ssd8(float l0, float l1, float l2, float l3, float l4, float l5, float l6, float l7,
+                                      float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7) {
+  // ComputeSsdPattern8Sse (:435-453): sub, mul, hadd, hadd, movehl + add
+  float d0 = __fsub_rn(l0, r0), d1 = __fsub_rn(l1, r1), d2 = __fsub_rn(l2, r2), d3 = __fsub_rn(l3, r3),
+        d4 = __fsub_rn(l4, r4), d5 = __fsub_rn(l5, r5), d6 = __fsub_rn(l6, r6), d7 = __fsub_rn(l7, r7);
+  d0 = __fmul_rn(d0, d0); d1 = __fmul_rn(d1, d1); d2 = __fmul_rn(d2, d2); d3 = __fmul_rn(d3, d3);
+  d4 = __fmul_rn(d4, d4); d5 = __fmul_rn(d5, d5); d6 = __fmul_rn(d6, d6); d7 = __fmul_rn(d7, d7);
+  return __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)), __fadd_rn(__fadd_rn(d4, d5), __fadd_rn(d6, d7)));
+}
 
 __global__ void __launch_bounds__(kDispThreads) k_disparity(int W, int H, odo_depth_params p, DepthWork d) {
-  extern __shared__ float s_rows[];  // [5][pitch] right rows y-2 .. y+2
-  const int b = blockIdx.z;
-  const int bnd = p.boundary;
-  const int y = bnd + blockIdx.y;
-  const int x0 = bnd + kSegW * blockIdx.x;
+  extern __shared__ float s_rows[];  // [kStagedRows][pitch] right rows y0-2 .. y1+2 of the current chunk
+  __shared__ int s_xy[kSelMax];
+  __shared__ int s_g[kSelMax + 1];   // group start indices
+  __shared__ int s_ng, s_xmax;
+  const int b = blockIdx.y, item = blockIdx.x;
+  const int cnt = d.sel_count[(int64_t)b * d.n_items + item];
+  if (cnt <= 0) return;
+  const int* list = d.sel_xy + ((int64_t)b * d.n_items + item) * kSelMax;
   const int64_t npx = (int64_t)W * H;
-  const uint8_t* val = d.val + b * npx + (int64_t)y * W;
-  __shared__ unsigned s_mask[2];
-  if (threadIdx.x < 64) {
-    const int x = x0 + threadIdx.x;
-    const bool sel = (x < W - bnd) && (val[x] != 0);
-    const unsigned m = __ballot_sync(0xffffffffu, sel);
-    if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = m;
+  const int bnd = p.boundary;
+  if (threadIdx.x < cnt) s_xy[threadIdx.x] = list[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // groups of <= kDispP consecutive list entries that share an image row
+    int ng = 0, run = 0, ycur = -1, xmax = 0;
+    for (int k = 0; k < cnt; k++) {
+      const int y = s_xy[k] >> 16, x = s_xy[k] & 0xffff;
+      xmax = max(xmax, x);
+      if (y != ycur || run == kDispP) {
+        s_g[ng++] = k;
+        run = 0;
+        ycur = y;
+      }
+      run++;
+    }
+    s_g[ng] = cnt;
+    s_ng = ng;
+    s_xmax = xmax;
   }
   __syncthreads();
-  const unsigned m0 = s_mask[0], m1 = s_mask[1];
-  if ((m0 | m1) == 0u) return;
-  const int xmax = x0 + (m1 ? 63 - __clz(m1) : 31 - __clz(m0));
-  const int pitch = W;
-  // stage columns [0, xmax + 2] (candidates end at xmax-1, taps reach +2) of the five right rows
-  const int ncol = min(xmax + 3, W);
+  const int ng = s_ng;
+  const int ymin = s_xy[0] >> 16, ymax = s_xy[cnt - 1] >> 16;
+  const int pitch = W + 4;
+  const int ncol = min(s_xmax + 3, W);  // candidates end at xmax-1, taps reach +2
   const float* br = d.blurR + b * npx;
-  for (int r = 0; r < 5; r++) {
-    const float* src = br + (int64_t)(y - 2 + r) * W;
-    float* dst = s_rows + r * pitch;
-    for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const float* rpp = s_rows;
-  const float* rp = s_rows + pitch;
-  const float* rc = s_rows + 2 * pitch;
-  const float* rn = s_rows + 3 * pitch;
-  const float* rnn = s_rows + 4 * pitch;
   const float* bl = d.blurL + b * npx;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int count = __popc(m0) + __popc(m1);
-  for (int k = wid; k < count; k += kDispThreads / 32) {
-    // x of the k-th selected pixel of the segment
-    int x;
-    {
-      const int c0 = __popc(m0);
-      unsigned m = (k < c0) ? m0 : m1;
-      int kk = (k < c0) ? k : k - c0;
-      for (int j = 0; j < kk; j++) m &= m - 1u;
-      x = x0 + ((k < c0) ? 0 : 32) + (__ffs(m) - 1);
+  for (int y0 = ymin; y0 <= ymax; y0 += kRowsPerChunk) {
+    const int y1 = min(y0 + kRowsPerChunk - 1, ymax);
+    // skip chunks without pixels (lists of the test hook may be sparse in y)
+    bool any = false;
+    for (int g = 0; g < ng && !any; g++) {
+      const int y = s_xy[s_g[g]] >> 16;
+      any = (y >= y0 && y <= y1);
     }
-    // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
-    const float l0 = __ldg(bl + (int64_t)(y + 2) * W + x), l1 = __ldg(bl + (int64_t)(y + 1) * W + x - 1),
-                l2 = __ldg(bl + (int64_t)y * W + x + 2), l3 = __ldg(bl + (int64_t)y * W + x),
-                l4 = __ldg(bl + (int64_t)y * W + x - 2), l5 = __ldg(bl + (int64_t)(y - 1) * W + x + 1),
-                l6 = __ldg(bl + (int64_t)(y - 1) * W + x - 1), l7 = __ldg(bl + (int64_t)(y - 2) * W + x);
-    float best = 1e+10f;
-    int best_rx = -1;
-#pragma unroll 2
-    for (int rx = bnd + lane; rx < x; rx += 32) {
-      // ComputeSsdPattern8Sse (:435-453): sub, mul, hadd, hadd, movehl+add
-      float d0 = __fsub_rn(l0, rnn[rx]), d1 = __fsub_rn(l1, rn[rx - 1]), d2 = __fsub_rn(l2, rc[rx + 2]),
-            d3 = __fsub_rn(l3, rc[rx]), d4 = __fsub_rn(l4, rc[rx - 2]), d5 = __fsub_rn(l5, rp[rx + 1]),
-            d6 = __fsub_rn(l6, rp[rx - 1]), d7 = __fsub_rn(l7, rpp[rx]);
-      d0 = __fmul_rn(d0, d0); d1 = __fmul_rn(d1, d1); d2 = __fmul_rn(d2, d2); d3 = __fmul_rn(d3, d3);
-      d4 = __fmul_rn(d4, d4); d5 = __fmul_rn(d5, d5); d6 = __fmul_rn(d6, d6); d7 = __fmul_rn(d7, d7);
-      const float ssd = __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)),
-                                  __fadd_rn(__fadd_rn(d4, d5), __fadd_rn(d6, d7)));
-      if (ssd < best) {  // strict '<' in ascending rx: first minimum wins (:385-386)
-        best = ssd;
-        best_rx = rx;
-      }
+    if (!any) continue;
+    __syncthreads();
+    const int nrows = y1 - y0 + 5;
+    for (int r = 0; r < nrows; r++) {
+      const int yy = y0 - 2 + r;
+      if (yy < 0 || yy >= H) continue;
+      const float* src = br + (int64_t)yy * W;
+      float* dst = s_rows + r * pitch;
+      for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
     }
-    // warp argmin: smaller cost, ties to the smaller column
+    __syncthreads();
+    for (int g = wid; g < ng; g += kDispWarps) {
+      const int k0 = s_g[g], n = s_g[g + 1] - k0;
+      const int y = s_xy[k0] >> 16;
+      if (y < y0 || y > y1) continue;
+      int xs[kDispP];
+      float l[kDispP][8];
+      int xg = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int orx = __shfl_xor_sync(0xffffffffu, best_rx, o);
-      const bool take = (orx >= 0) && (best_rx < 0 || ob < best || (ob == best && orx < best_rx));
-      if (take) {
-        best = ob;
-        best_rx = orx;
+      for (int i = 0; i < kDispP; i++) {
+        xs[i] = (i < n) ? (s_xy[k0 + i] & 0xffff) : 0;
+        xg = max(xg, xs[i]);
+        const int x = (i < n) ? xs[i] : (s_xy[k0] & 0xffff);
+        // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
+        l[i][0] = __ldg(bl + (int64_t)(y + 2) * W + x);
+        l[i][1] = __ldg(bl + (int64_t)(y + 1) * W + x - 1);
+        l[i][2] = __ldg(bl + (int64_t)y * W + x + 2);
+        l[i][3] = __ldg(bl + (int64_t)y * W + x);
+        l[i][4] = __ldg(bl + (int64_t)y * W + x - 2);
+        l[i][5] = __ldg(bl + (int64_t)(y - 1) * W + x + 1);
+        l[i][6] = __ldg(bl + (int64_t)(y - 1) * W + x - 1);
+        l[i][7] = __ldg(bl + (int64_t)(y - 2) * W + x);
       }
-    }
-    if (lane == 0) {
-      const int64_t o = b * npx + (int64_t)y * W + x;
-      if (d.min_ssd) d.min_ssd[o] = best;
-      if (!(best > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
-        const float disp = (float)abs(x - best_rx);
-        d.disp[o] = disp;
-        d.dep[o] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
-        if (d.match_x) d.match_x[o] = best_rx;
-        atomicAdd(&d.stats[b].n_matched, 1);
+      const float* rpp = s_rows + (y - y0) * pitch;
+      const float* rp = rpp + pitch;
+      const float* rc = rp + pitch;
+      const float* rn = rc + pitch;
+      const float* rnn = rn + pitch;
+      float best[kDispP];
+      int brx[kDispP];
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+        best[i] = 1e+10f;
+        brx[i] = -1;
+      }
+      for (int rx = bnd + lane; rx < xg; rx += 32) {
+        const float r0 = rnn[rx], r1 = rn[rx - 1], r2 = rc[rx + 2], r3 = rc[rx], r4 = rc[rx - 2], r5 = rp[rx + 1],
+                    r6 = rp[rx - 1], r7 = rpp[rx];
+#pragma unroll
+        for (int i = 0; i < kDispP; i++) {
+          const float ssd = ssd8(l[i][0], l[i][1], l[i][2], l[i][3], l[i][4], l[i][5], l[i][6], l[i][7], r0, r1, r2,
+                                 r3, r4, r5, r6, r7);
+          // candidates of pixel i are right_x = boundary .. x_i - 1; strict '<' in ascending rx keeps
+          // the FIRST minimum (:382-386)
+          if (rx < xs[i] && ssd < best[i]) {
+            best[i] = ssd;
+            brx[i] = rx;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+        // warp argmin: smaller cost, ties to the smaller column
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+          const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
+          const bool take = (orx >= 0) && (brx[i] < 0 || ob < best[i] || (ob == best[i] && orx < brx[i]));
+          if (take) {
+            best[i] = ob;
+            brx[i] = orx;
+          }
+        }
+        if (lane == i && i < n) {
+          const int x = xs[i];
+          const int64_t o = b * npx + (int64_t)y * W + x;
+          if (d.min_ssd) d.min_ssd[o] = best[i];
+          if (!(best[i] > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+            const float disp = (float)abs(x - brx[i]);
+            d.disp[o] = disp;
+            d.dep[o] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+            if (d.match_x) d.match_x[o] = brx[i];
+            atomicAdd(&d.stats[b].n_matched, 1);
+          }
+        }
       }
     }
   }
 }
 
 // ---- inverse-depth refinement ---------------------------------------------------------------------------
+// One pass over the pixel list per LM iteration: the update decided by the previous iteration's GLOBAL
+// accept/reject (:147-165) is applied to a slot and the new tmp_depth is evaluated (:200-242) in the same
+// visit, so a slot costs one dependent chain of global accesses per iteration; kRefUnroll independent
+// slots per thread keep that many chains in flight.
 constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
+constexpr int kRefUnroll = 4;
 
 struct RefShared {
   double warp[kRefWarps][32];
   double tot[32];
 };
 
-__global__ void __launch_bounds__(kRefThreads, 1) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
+enum { PEND_NONE = 0, PEND_ACCEPT = 1, PEND_REJECT = 2 };
+
+__global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
                                                           int64_t stride, int W, int H, odo_depth_params p,
                                                           DepthWork d, double* partials, unsigned* barrier,
                                                           int* abort_flag) {
@@ -243,111 +312,125 @@ __global__ void __launch_bounds__(kRefThreads, 1) k_refine(const float* __restri
   gs.parity = 0;
   gs.G = G;
   const int64_t npx = (int64_t)W * H;
-  const float* L = Limg + b * stride;
-  const float* R = Rimg + b * stride;
+  const float* __restrict__ L = Limg + b * stride;
+  const float* __restrict__ R = Rimg + b * stride;
   float* dep = d.dep + b * npx;
   uint8_t* val = d.val + b * npx;
   // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
   const int nslots = d.cap;
-  const int* sel_xy = d.sel_xy + (int64_t)b * nslots;
+  const int* __restrict__ sel_xy = d.sel_xy + (int64_t)b * nslots;
   float* st_cur = d.ref_state + (int64_t)b * 6 * nslots;
-  float* st_pre = st_cur + nslots;
-  float* st_tmp = st_pre + nslots;
+  float* st_tmp = st_cur + nslots;
   float* st_res = st_tmp + nslots;
   float* st_jt = st_res + nslots;
   float* st_bv = st_jt + nslots;
   odo_depth_stats* stats = d.stats + b;
   const int tid = blockIdx.x * kRefThreads + threadIdx.x;
   const int nthreads = G * kRefThreads;
-  const int n_sel = stats->n_selected;  // written by k_select (previous launch)
+  const int n_sel = stats->n_selected;            // written by k_select (previous launch)
   const bool too_many = n_sel > p.max_residuals;  // quirk Q7: the reference would overflow init_depth
 
-  // init: init_depth / current_depth / tmp_depth, :105-139
-  for (int s = tid; s < nslots; s += nthreads) {
-    const int yx = sel_xy[s];
-    if (yx < 0) continue;
-    const float v = dep[(int64_t)(yx >> 16) * W + (yx & 0xffff)];
-    st_cur[s] = v;
-    st_tmp[s] = v;
-    st_pre[s] = 0.f;
-    st_res[s] = 0.f;
-  }
   float lambda = p.lambda;
   float err_last = 1e+10f, err_now = 0.f;
   int iter_count = 0;
+  int pending = PEND_NONE;      // decision of the previous iteration, not yet applied to the slots
+  bool accepted_once = false;   // pre_depth is all zeros until the first accepted estimate
+  bool first = true;
   const float txfx = __fmul_rn(p.baseline, p.fx);  // tx * fx
   const float gscale = __fmul_rn(txfx, 0.5f);
+  const float wmax = (float)(W - 2);
   while (!too_many && p.max_iters > iter_count) {
-    // ComputeResidualJacobian(tmp_depth), :200-242
     double acc[2] = {0.0, 0.0};
-    for (int s = tid; s < nslots; s += nthreads) {
-      const int yx = sel_xy[s];
-      if (yx < 0) continue;
-      const int y = yx >> 16, x = yx & 0xffff;
-      const float wf = floorf(__fsub_rn((float)x, __fmul_rn(txfx, st_tmp[s])));
-      if (!(wf >= 2.0f && wf <= (float)(W - 2))) {  // also catches NaN (int(NaN) is INT_MIN on x86)
-        st_jt[s] = 0.f;
-        st_bv[s] = 0.f;
-        st_res[s] = -1000.f;
-        continue;
+    for (int s0 = tid; s0 < nslots; s0 += nthreads * kRefUnroll) {
+      int yx[kRefUnroll];
+      float cur[kRefUnroll], tmp[kRefUnroll], jt[kRefUnroll], bv[kRefUnroll], lv[kRefUnroll];
+#pragma unroll
+      for (int u = 0; u < kRefUnroll; u++) {
+        const int s = s0 + u * nthreads;
+        yx[u] = (s < nslots) ? sel_xy[s] : -1;
       }
-      const int wx = (int)wf;
-      const float* rrow = R + (int64_t)y * W;
-      const float r_i = __fsub_rn(__ldg(L + (int64_t)y * W + x), __ldg(rrow + wx));
-      const float ar = fabsf(r_i);
-      const float w_i = (ar <= p.huber_delta) ? 1.0f : __fdiv_rn(p.huber_delta, ar);
-      const float g = __fmul_rn(gscale, __fsub_rn(__ldg(rrow + wx + 1), __ldg(rrow + wx - 1)));
-      st_res[s] = ar;
-      acc[0] += (double)__fmul_rn(__fmul_rn(r_i, r_i), w_i);
-      acc[1] += 1.0;
-      st_jt[s] = __fmul_rn(__fmul_rn(g, g), w_i);
-      st_bv[s] = __fmul_rn(__fmul_rn(-g, w_i), r_i);
+#pragma unroll
+      for (int u = 0; u < kRefUnroll; u++) {
+        const int s = s0 + u * nthreads;
+        cur[u] = tmp[u] = jt[u] = bv[u] = lv[u] = 0.f;
+        if (yx[u] >= 0) {
+          const int64_t o = (int64_t)(yx[u] >> 16) * W + (yx[u] & 0xffff);
+          lv[u] = __ldg(L + o);
+          if (first) {
+            cur[u] = tmp[u] = dep[o];  // init_depth / current_depth / tmp_depth, :105-139
+          } else {
+            cur[u] = st_cur[s];
+            tmp[u] = st_tmp[s];
+            jt[u] = st_jt[s];
+            bv[u] = st_bv[s];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRefUnroll; u++) {
+        if (yx[u] < 0) continue;
+        const int s = s0 + u * nthreads;
+        const int y = yx[u] >> 16, x = yx[u] & 0xffff;
+        if (pending == PEND_ACCEPT) cur[u] = tmp[u];                    // current = tmp ; pre = current
+        else if (pending == PEND_REJECT && !accepted_once) cur[u] = 0.f;  // current = pre (still zero)
+        if (pending != PEND_NONE) {
+          // A = jtwj + lambda*jtwj ; delta = A.inverse() * b ; tmp = delta + current, :162-165
+          const float A = __fadd_rn(jt[u], __fmul_rn(lambda, jt[u]));
+          tmp[u] = __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, A), bv[u]), cur[u]);
+        }
+        // ComputeResidualJacobian(tmp_depth), :200-242
+        const float wf = floorf(__fsub_rn((float)x, __fmul_rn(txfx, tmp[u])));
+        float res, njt = 0.f, nbv = 0.f;
+        if (!(wf >= 2.0f && wf <= wmax)) {  // also catches NaN (int(NaN) is INT_MIN on x86, i.e. "< 2")
+          res = -1000.f;
+        } else {
+          const float* rrow = R + (int64_t)y * W + (int)wf;
+          const float r_i = __fsub_rn(lv[u], __ldg(rrow));
+          const float ar = fabsf(r_i);
+          const float w_i = (ar <= p.huber_delta) ? 1.0f : __fdiv_rn(p.huber_delta, ar);
+          const float g = __fmul_rn(gscale, __fsub_rn(__ldg(rrow + 1), __ldg(rrow - 1)));
+          res = ar;
+          acc[0] += (double)__fmul_rn(__fmul_rn(r_i, r_i), w_i);
+          acc[1] += 1.0;
+          njt = __fmul_rn(__fmul_rn(g, g), w_i);
+          nbv = __fmul_rn(__fmul_rn(-g, w_i), r_i);
+        }
+        st_cur[s] = cur[u];
+        st_tmp[s] = tmp[u];
+        st_res[s] = res;
+        st_jt[s] = njt;
+        st_bv[s] = nbv;
+      }
     }
+    first = false;
+    if (pending == PEND_ACCEPT) accepted_once = true;
     group_allreduce<2, kRefWarps>(acc, sh.warp, sh.tot, gs);
     err_now = (float)(sh.tot[0] / sh.tot[1]);
     __syncthreads();
-    if (*(volatile int*)abort_flag) break;
-    bool reject = false, stop = false;
+    if (*(volatile int*)abort_flag) { pending = PEND_NONE; break; }
     if (err_now > err_last) {  // :147-151
       lambda = lambda * 10.0f;
-      if (lambda > 1e+5f) break;
-      reject = true;
+      if (lambda > 1e+5f) { pending = PEND_NONE; break; }  // break BEFORE current = pre
+      pending = PEND_REJECT;
     } else {                   // :152-159
+      pending = PEND_ACCEPT;
       const float err_diff = err_now / err_last;
-      if (err_diff > p.precision) stop = true;
-      else {
-        err_last = err_now;
-        lambda = fmaxf(lambda / 10.0f, 1e-7f);
-      }
+      if (err_diff > p.precision) break;                   // break AFTER current = tmp
+      err_last = err_now;
+      lambda = fmaxf(lambda / 10.0f, 1e-7f);
     }
-    for (int s = tid; s < nslots; s += nthreads) {
-      if (sel_xy[s] < 0) continue;
-      float cur;
-      if (reject) {
-        cur = st_pre[s];
-      } else {
-        cur = st_tmp[s];
-        st_pre[s] = cur;
-      }
-      st_cur[s] = cur;
-      if (!stop) {
-        // A = jtwj + lambda*jtwj ; delta = A.inverse() * b ; tmp = delta + current, :162-165
-        const float jt = st_jt[s];
-        const float A = __fadd_rn(jt, __fmul_rn(lambda, jt));
-        const float delta = __fmul_rn(__fdiv_rn(1.0f, A), st_bv[s]);
-        st_tmp[s] = __fadd_rn(delta, cur);
-      }
-    }
-    if (stop) break;
     iter_count++;
   }
-  // write-back and filters, :176-191
+  // apply the last decision to current_depth, then write-back and filters, :176-191
   double nv[1] = {0.0};
   for (int s = tid; s < nslots && !too_many; s += nthreads) {
     const int yx = sel_xy[s];
     if (yx < 0) continue;
     const int64_t o = (int64_t)(yx >> 16) * W + (yx & 0xffff);
-    const float res = st_res[s], cur = st_cur[s];
+    float cur = first ? dep[o] : st_cur[s];
+    const float res = first ? 0.f : st_res[s];
+    if (pending == PEND_ACCEPT) cur = st_tmp[s];
+    else if (pending == PEND_REJECT && !accepted_once) cur = 0.f;
     bool ok;
     if (res > p.photo_th || res == -1000.f) ok = false;
     else {
@@ -410,6 +493,7 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->stats = (odo_depth_stats*)p; p += al((size_t)batch * sizeof(odo_depth_stats));
   d->ref_state = (float*)p;
   d->cap = kGridBlocks * kSelMax;
+  d->n_items = kGridBlocks;
 }
 
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
@@ -429,24 +513,25 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
 }
 
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
-  const int rows = h - 2 * p.boundary;
-  const int segs = (w - 2 * p.boundary + kSegW - 1) / kSegW;
-  if (rows <= 0 || segs <= 0) return;
-  const size_t smem = sizeof(float) * 5 * (size_t)w;
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    cudaFuncSetAttribute(k_disparity, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+  if (d.n_items <= 0) return;
+  const size_t smem = sizeof(float) * kStagedRows * (size_t)(w + 4);
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    cudaFuncSetAttribute(k_disparity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = smem;
   }
-  k_disparity<<<dim3(segs, rows, batch), kDispThreads, smem, c->stream>>>(w, h, p, d);
+  k_disparity<<<dim3(d.n_items, batch), kDispThreads, smem, c->stream>>>(w, h, p, d);
   c->launches++;
 }
 
 // scratch for the refinement's group reduction lives behind the refinement state
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch) {
-  int G = c->sm_count / (batch > 0 ? batch : 1);
-  const int gmax = (kGridBlocks * kSelMax + kRefThreads - 1) / kRefThreads;  // one slot per thread
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int G = (c->sm_count * per_sm) / (batch > 0 ? batch : 1);
+  const int gmax = (d.cap + kRefThreads - 1) / kRefThreads;  // one slot per thread
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   // partials / barrier / abort flag: carved from a small dedicated allocation owned by the context

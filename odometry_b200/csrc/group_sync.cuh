@@ -49,15 +49,40 @@ __device__ __forceinline__ void group_barrier(GroupSync& gs) {
 
 // sums vals[0..NV) over all threads of all G CTAs of the sequence in a fixed order; the totals end up
 // in s_tot[0..NV) of every CTA.  s_warp: [WARPS][32] doubles of shared memory.
+// Transposed butterfly: reduces 32 per-lane values across the warp with 31 exchanges (instead of
+// 32 x 5); afterwards lane i holds the warp total of value i in v[0].  Fixed order => deterministic.
+template <int HALF>
+__device__ __forceinline__ void transpose_reduce_step(double* v, int lane) {
+  const bool up = (lane & HALF) != 0;
+#pragma unroll
+  for (int i = 0; i < HALF; i++) {
+    const double send = up ? v[i] : v[i + HALF];
+    const double keep = up ? v[i + HALF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+  }
+}
+
 template <int NV, int WARPS>
 __device__ __forceinline__ void group_allreduce(double* vals, double (*s_warp)[32], double* s_tot, GroupSync& gs) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (NV > 8) {
+    double v[32];
 #pragma unroll
-  for (int k = 0; k < NV; k++) {
-    double v = vals[k];
+    for (int k = 0; k < 32; k++) v[k] = (k < NV) ? vals[k] : 0.0;
+    transpose_reduce_step<16>(v, lane);
+    transpose_reduce_step<8>(v, lane);
+    transpose_reduce_step<4>(v, lane);
+    transpose_reduce_step<2>(v, lane);
+    transpose_reduce_step<1>(v, lane);
+    s_warp[wid][lane] = v[0];
+  } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_warp[wid][k] = v;
+    for (int k = 0; k < NV; k++) {
+      double v = vals[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_warp[wid][k] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < NV) {
