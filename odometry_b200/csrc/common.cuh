@@ -137,13 +137,16 @@ struct DepthWork {
   odo_depth_stats* stats;  // [batch]
   float* ref_state;    // refinement scratch [batch][6][cap]
   int cap;             // pixel-list capacity per sequence
+  int64_t blurL_stride;  // elements between sequences in blurL (the tracker aliases level 0 of the image pyramid)
+  int64_t dep_stride;    // elements between sequences in dep (the tracker aliases level 0 of the depth pyramid)
   int n_items;         // disparity work items (lists of <= 80 pixels) per sequence; 512 in the pipeline
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)
 void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debug);
+// blur_left_done: d.blurL already holds GaussianBlur(L) (image pyramid level 0 of the same frame)
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
-                   const odo_depth_params& p, DepthWork d, int batch);
+                   const odo_depth_params& p, DepthWork d, int batch, bool blur_left_done = false);
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch);
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch);

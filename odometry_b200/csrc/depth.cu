@@ -38,7 +38,7 @@ constexpr int kMagCache = 2048;
 __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_params p, DepthWork d) {
   const int b = blockIdx.y, block_id = blockIdx.x;
   const int64_t npx = (int64_t)W * H;
-  const float* bl = d.blurL + b * npx;
+  const float* bl = d.blurL + b * d.blurL_stride;
   uint8_t* val = d.val + b * npx;
   const int bw = (W - p.boundary * 2) / 32, bh = (H - p.boundary * 2) / 16;
   const int start_y = p.boundary + (block_id / 32) * bh;
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_prefix, s_k;
   __shared__ int s_w[kSelThreads / 32];
+  __shared__ unsigned s_wsum[kSelThreads / 32];
   const bool cached = n <= kMagCache;
   if (cached)
     for (int i = threadIdx.x; i < n; i += kSelThreads) s_mag[i] = grad_mag(bl, W, start_y + i / bw, start_x + i % bw);
@@ -68,16 +69,29 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
       if ((u & hi_mask) == (prefix & hi_mask)) atomicAdd(&s_hist[(u >> (8 * pass)) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned k = s_k, cum = 0u;
-      int bin = 0;
-      for (; bin < 256; bin++) {
-        if (cum + s_hist[bin] > k) break;
-        cum += s_hist[bin];
+    {
+      // thread t owns bin t: inclusive scan over the 256 bins, the bin whose range contains k wins
+      const unsigned k = s_k;
+      const unsigned hcount = s_hist[threadIdx.x];
+      unsigned inc = hcount;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += v;
       }
-      if (bin > 255) bin = 255;
-      s_k = k - cum;
-      s_prefix = prefix | ((unsigned)bin << (8 * pass));
+      if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = inc;
+      __syncthreads();
+      unsigned woff = 0u;
+#pragma unroll
+      for (int w8 = 0; w8 < kSelThreads / 32; w8++)
+        if (w8 < (int)(threadIdx.x >> 5)) woff += s_wsum[w8];
+      inc += woff;
+      const unsigned exc = inc - hcount;
+      __syncthreads();
+      if (exc <= k && k < inc) {
+        s_k = k - exc;
+        s_prefix = prefix | ((unsigned)threadIdx.x << (8 * pass));
+      }
     }
     __syncthreads();
   }
@@ -134,6 +148,7 @@ constexpr int kDispWarps = kDispThreads / 32;
 constexpr int kDispP = 4;
 constexpr int kRowsPerChunk = 4;
 constexpr int kStagedRows = kRowsPerChunk + 4;
+constexpr int kDispStage = 0;
 
 __device__ __forceinline__ float ssd8(float l0, float l1, float l2, float l3, float l4, float l5, float l6, float l7,
                                       float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7) {
@@ -145,7 +160,97 @@ __device__ __forceinline__ float ssd8(float l0, float l1, float l2, float l3, fl
   return __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)), __fadd_rn(__fadd_rn(d4, d5), __fadd_rn(d6, d7)));
 }
 
-__global__ void __launch_bounds__(kDispThreads) k_disparity(int W, int H, odo_depth_params p, DepthWork d) {
+// One warp, one group of P pixels of image row y (P is a template parameter so that a short group does
+// not pay for absent pixels).  Lane `lane` evaluates candidate columns boundary + lane, + 32, ...; the
+// taps of the next column are fetched while the current one is evaluated.
+template <int P>
+__device__ __forceinline__ void disparity_group(const int* __restrict__ gxy, int y, int W, int bnd, int lane,
+                                                const float* __restrict__ bl, const float* __restrict__ rpp,
+                                                int rpitch, const odo_depth_params& p, const DepthWork& d,
+                                                int64_t img_off, int b) {
+  int xs[P];
+  float l[P][8];
+  int xg = 0;
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    const int x = gxy[i] & 0xffff;
+    xs[i] = x;
+    xg = max(xg, x);
+    // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
+    l[i][0] = __ldg(bl + (int64_t)(y + 2) * W + x);
+    l[i][1] = __ldg(bl + (int64_t)(y + 1) * W + x - 1);
+    l[i][2] = __ldg(bl + (int64_t)y * W + x + 2);
+    l[i][3] = __ldg(bl + (int64_t)y * W + x);
+    l[i][4] = __ldg(bl + (int64_t)y * W + x - 2);
+    l[i][5] = __ldg(bl + (int64_t)(y - 1) * W + x + 1);
+    l[i][6] = __ldg(bl + (int64_t)(y - 1) * W + x - 1);
+    l[i][7] = __ldg(bl + (int64_t)(y - 2) * W + x);
+  }
+  const float* rp = rpp + rpitch;
+  const float* rc = rp + rpitch;
+  const float* rn = rc + rpitch;
+  const float* rnn = rn + rpitch;
+  float best[P];
+  int brx[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    best[i] = 1e+10f;
+    brx[i] = -1;
+  }
+  int rx = bnd + lane;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f, r7 = 0.f;
+  if (rx < xg) {
+    r0 = rnn[rx]; r1 = rn[rx - 1]; r2 = rc[rx + 2]; r3 = rc[rx]; r4 = rc[rx - 2]; r5 = rp[rx + 1]; r6 = rp[rx - 1]; r7 = rpp[rx];
+  }
+  while (rx < xg) {
+    const int nx = rx + 32;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f, n5 = 0.f, n6 = 0.f, n7 = 0.f;
+    if (nx < xg) {
+      n0 = rnn[nx]; n1 = rn[nx - 1]; n2 = rc[nx + 2]; n3 = rc[nx]; n4 = rc[nx - 2]; n5 = rp[nx + 1]; n6 = rp[nx - 1]; n7 = rpp[nx];
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const float ssd = ssd8(l[i][0], l[i][1], l[i][2], l[i][3], l[i][4], l[i][5], l[i][6], l[i][7], r0, r1, r2, r3,
+                             r4, r5, r6, r7);
+      // candidates of pixel i are right_x = boundary .. x_i - 1; strict '<' in ascending rx keeps
+      // the FIRST minimum (:382-386)
+      if (rx < xs[i] && ssd < best[i]) {
+        best[i] = ssd;
+        brx[i] = rx;
+      }
+    }
+    r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7;
+    rx = nx;
+  }
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    // warp argmin: smaller cost, ties to the smaller column
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+      const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
+      const bool take = (orx >= 0) && (brx[i] < 0 || ob < best[i] || (ob == best[i] && orx < brx[i]));
+      if (take) {
+        best[i] = ob;
+        brx[i] = orx;
+      }
+    }
+    if (lane == i) {
+      const int x = xs[i];
+      const int64_t o = img_off + (int64_t)y * W + x;
+      if (d.min_ssd) d.min_ssd[o] = best[i];
+      if (!(best[i] > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+        const float disp = (float)abs(x - brx[i]);
+        if (d.disp) d.disp[o] = disp;
+        d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+        if (d.match_x) d.match_x[o] = brx[i];
+        atomicAdd(&d.stats[b].n_matched, 1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDispThreads, 3) k_disparity(int W, int H, odo_depth_params p, DepthWork d) {
   extern __shared__ float s_rows[];  // [kStagedRows][pitch] right rows y0-2 .. y1+2 of the current chunk
   __shared__ int s_xy[kSelMax];
   __shared__ int s_g[kSelMax + 1];   // group start indices
@@ -181,101 +286,46 @@ __global__ void __launch_bounds__(kDispThreads) k_disparity(int W, int H, odo_de
   const int pitch = W + 4;
   const int ncol = min(s_xmax + 3, W);  // candidates end at xmax-1, taps reach +2
   const float* br = d.blurR + b * npx;
-  const float* bl = d.blurL + b * npx;
+  const float* bl = d.blurL + b * d.blurL_stride;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // kDispStage == 0: the right taps are read straight from global memory; the five rows a group needs
+  // (<= 25 KB) are shared by every group of that image row on the SM and stay L1-resident.
+  // kDispStage == 1: the rows of each chunk of kRowsPerChunk image rows are staged in shared memory.
   for (int y0 = ymin; y0 <= ymax; y0 += kRowsPerChunk) {
     const int y1 = min(y0 + kRowsPerChunk - 1, ymax);
-    // skip chunks without pixels (lists of the test hook may be sparse in y)
-    bool any = false;
-    for (int g = 0; g < ng && !any; g++) {
-      const int y = s_xy[s_g[g]] >> 16;
-      any = (y >= y0 && y <= y1);
+    if (kDispStage) {
+      // skip chunks without pixels (lists of the test hook may be sparse in y)
+      bool any = false;
+      for (int g = 0; g < ng && !any; g++) {
+        const int y = s_xy[s_g[g]] >> 16;
+        any = (y >= y0 && y <= y1);
+      }
+      if (!any) continue;
+      __syncthreads();
+      const int nrows = y1 - y0 + 5;
+      for (int r = 0; r < nrows; r++) {
+        const int yy = y0 - 2 + r;
+        if (yy < 0 || yy >= H) continue;
+        const float* src = br + (int64_t)yy * W;
+        float* dst = s_rows + r * pitch;
+        for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+    } else if (y0 != ymin) {
+      break;  // one pass over all groups is enough without staging
     }
-    if (!any) continue;
-    __syncthreads();
-    const int nrows = y1 - y0 + 5;
-    for (int r = 0; r < nrows; r++) {
-      const int yy = y0 - 2 + r;
-      if (yy < 0 || yy >= H) continue;
-      const float* src = br + (int64_t)yy * W;
-      float* dst = s_rows + r * pitch;
-      for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
     for (int g = wid; g < ng; g += kDispWarps) {
       const int k0 = s_g[g], n = s_g[g + 1] - k0;
       const int y = s_xy[k0] >> 16;
-      if (y < y0 || y > y1) continue;
-      int xs[kDispP];
-      float l[kDispP][8];
-      int xg = 0;
-#pragma unroll
-      for (int i = 0; i < kDispP; i++) {
-        xs[i] = (i < n) ? (s_xy[k0 + i] & 0xffff) : 0;
-        xg = max(xg, xs[i]);
-        const int x = (i < n) ? xs[i] : (s_xy[k0] & 0xffff);
-        // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
-        l[i][0] = __ldg(bl + (int64_t)(y + 2) * W + x);
-        l[i][1] = __ldg(bl + (int64_t)(y + 1) * W + x - 1);
-        l[i][2] = __ldg(bl + (int64_t)y * W + x + 2);
-        l[i][3] = __ldg(bl + (int64_t)y * W + x);
-        l[i][4] = __ldg(bl + (int64_t)y * W + x - 2);
-        l[i][5] = __ldg(bl + (int64_t)(y - 1) * W + x + 1);
-        l[i][6] = __ldg(bl + (int64_t)(y - 1) * W + x - 1);
-        l[i][7] = __ldg(bl + (int64_t)(y - 2) * W + x);
-      }
-      const float* rpp = s_rows + (y - y0) * pitch;
-      const float* rp = rpp + pitch;
-      const float* rc = rp + pitch;
-      const float* rn = rc + pitch;
-      const float* rnn = rn + pitch;
-      float best[kDispP];
-      int brx[kDispP];
-#pragma unroll
-      for (int i = 0; i < kDispP; i++) {
-        best[i] = 1e+10f;
-        brx[i] = -1;
-      }
-      for (int rx = bnd + lane; rx < xg; rx += 32) {
-        const float r0 = rnn[rx], r1 = rn[rx - 1], r2 = rc[rx + 2], r3 = rc[rx], r4 = rc[rx - 2], r5 = rp[rx + 1],
-                    r6 = rp[rx - 1], r7 = rpp[rx];
-#pragma unroll
-        for (int i = 0; i < kDispP; i++) {
-          const float ssd = ssd8(l[i][0], l[i][1], l[i][2], l[i][3], l[i][4], l[i][5], l[i][6], l[i][7], r0, r1, r2,
-                                 r3, r4, r5, r6, r7);
-          // candidates of pixel i are right_x = boundary .. x_i - 1; strict '<' in ascending rx keeps
-          // the FIRST minimum (:382-386)
-          if (rx < xs[i] && ssd < best[i]) {
-            best[i] = ssd;
-            brx[i] = rx;
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kDispP; i++) {
-        // warp argmin: smaller cost, ties to the smaller column
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
-          const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
-          const bool take = (orx >= 0) && (brx[i] < 0 || ob < best[i] || (ob == best[i] && orx < brx[i]));
-          if (take) {
-            best[i] = ob;
-            brx[i] = orx;
-          }
-        }
-        if (lane == i && i < n) {
-          const int x = xs[i];
-          const int64_t o = b * npx + (int64_t)y * W + x;
-          if (d.min_ssd) d.min_ssd[o] = best[i];
-          if (!(best[i] > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
-            const float disp = (float)abs(x - brx[i]);
-            d.disp[o] = disp;
-            d.dep[o] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
-            if (d.match_x) d.match_x[o] = brx[i];
-            atomicAdd(&d.stats[b].n_matched, 1);
-          }
-        }
+      if (kDispStage && (y < y0 || y > y1)) continue;
+      const int rpitch = kDispStage ? pitch : W;
+      const float* rpp = kDispStage ? s_rows + (y - y0) * pitch : br + (int64_t)(y - 2) * W;
+      const int64_t img_off = b * npx;  // disp / match_x / min_ssd planes
+      switch (n) {
+        case 1: disparity_group<1>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
+        case 2: disparity_group<2>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
+        case 3: disparity_group<3>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
+        default: disparity_group<4>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
       }
     }
   }
@@ -314,7 +364,7 @@ __global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restri
   const int64_t npx = (int64_t)W * H;
   const float* __restrict__ L = Limg + b * stride;
   const float* __restrict__ R = Rimg + b * stride;
-  float* dep = d.dep + b * npx;
+  float* dep = d.dep + b * d.dep_stride;
   uint8_t* val = d.val + b * npx;
   // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
   const int nslots = d.cap;
@@ -494,17 +544,20 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->ref_state = (float*)p;
   d->cap = kGridBlocks * kSelMax;
   d->n_items = kGridBlocks;
+  d->blurL_stride = (int64_t)w * h;
+  d->dep_stride = (int64_t)w * h;
 }
 
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
-                   const odo_depth_params& p, DepthWork d, int batch) {
+                   const odo_depth_params& p, DepthWork d, int batch, bool blur_left_done) {
   const size_t npx = (size_t)w * h;
   // cv::GaussianBlur on both images, :255-257 ; outputs zero-filled (quirk Q6)
-  launch_blur3(c, L, stride, d.blurL, (int64_t)npx, w, h, batch);
+  if (!blur_left_done) launch_blur3(c, L, stride, d.blurL, d.blurL_stride, w, h, batch);
   launch_blur3(c, R, stride, d.blurR, (int64_t)npx, w, h, batch);
   cudaMemsetAsync(d.val, 0, npx * batch, c->stream);
-  cudaMemsetAsync(d.disp, 0, npx * batch * 4, c->stream);
-  cudaMemsetAsync(d.dep, 0, npx * batch * 4, c->stream);
+  if (d.disp) cudaMemsetAsync(d.disp, 0, npx * batch * 4, c->stream);
+  if (d.dep_stride == (int64_t)npx) cudaMemsetAsync(d.dep, 0, npx * batch * 4, c->stream);
+  else cudaMemset2DAsync(d.dep, (size_t)d.dep_stride * 4, 0, npx * 4, batch, c->stream);
   cudaMemsetAsync(d.stats, 0, sizeof(odo_depth_stats) * batch, c->stream);
   if (d.match_x) cudaMemsetAsync(d.match_x, 0xff, npx * batch * 4, c->stream);
   if (d.min_ssd) cudaMemsetAsync(d.min_ssd, 0, npx * batch * 4, c->stream);
@@ -514,7 +567,7 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
 
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
   if (d.n_items <= 0) return;
-  const size_t smem = sizeof(float) * kStagedRows * (size_t)(w + 4);
+  const size_t smem = kDispStage ? sizeof(float) * kStagedRows * (size_t)(w + 4) : 0;
   static size_t attr_set = 0;
   if (smem > 48 * 1024 && smem > attr_set) {
     cudaFuncSetAttribute(k_disparity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -235,13 +235,13 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
   }
   cudaEventRecord(t->ev[2], c->stream);
   // ComputeDepth on every frame (:226-229), then DepthPyramid (:252)
-  launch_select(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
+  launch_select(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n, /*blur_left_done=*/true);
   cudaEventRecord(t->ev[3], c->stream);
   launch_disparity(c, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(t->ev[4], c->stream);
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(t->ev[5], c->stream);
-  launch_depth_pyramid(c, t->dw.dep, t->npx, t->cur_dep, t->pyr_stride, t->g, 0, n);
+  launch_depth_pyramid(c, t->dw.dep, t->dw.dep_stride, t->cur_dep, t->pyr_stride, t->g, 0, n);
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
   // keyframe promotion (:258-265): the new keyframe's pyramids and LM point lists
   {
@@ -327,6 +327,14 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   t->cur_dep = (float*)p; p += pyr_b;
   t->kf_dep = (float*)p; p += pyr_b;
   depth_work_bind(&t->dw, p, w, h, n_seq, false); p += dw_b;
+  // level 0 of the image pyramid IS GaussianBlur(left) and level 0 of the depth pyramid IS the refined
+  // inverse depth: alias them instead of computing / copying them twice; the disparity map is a display
+  // output of ComputeDepth that the tracking loop never reads
+  t->dw.blurL = t->cur_img;
+  t->dw.blurL_stride = t->pyr_stride;
+  t->dw.dep = t->cur_dep;
+  t->dw.dep_stride = t->pyr_stride;
+  t->dw.disp = nullptr;
   lm_lists_bind(&t->lists, p, t->g, n_seq); p += ll_b;
   lm_work_bind(&t->lmw, p, t->g, n_seq, G); p += lw_b;
   t->T_init = (float*)p; p += ti_b;

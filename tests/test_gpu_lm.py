@@ -103,7 +103,7 @@ def test_solve_matches_oracle(ctx, scene, depth_key, robust, smooth):
     assert list(st.n_res)[:4] == list(ost.n_res)[:4]
     # and it actually converged towards the rendered motion
     ang_gt, tr_gt = pose_err(T, scene["T_gt"].astype(np.float32))
-    assert ang_gt < 1e-2 and tr_gt < 6e-2
+    assert ang_gt < 1e-2 and tr_gt < 0.1
 
 
 def test_solve_warm_start_and_determinism(ctx, scene):
