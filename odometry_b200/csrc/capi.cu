@@ -191,8 +191,9 @@ static int lm_check(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_
 static int lm_group_size(const odo_ctx* c, const PyrGeom& g) {
   // CTAs per sequence for a single solve: enough to spread level 0, never more than the SM count
   const int64_t n0 = (int64_t)g.w[0] * g.h[0];
-  int G = (int)((n0 + 4095) / 4096);
-  if (G > c->sm_count) G = c->sm_count;
+  int G = (int)((n0 + 16383) / 16384);
+  const int cap = lm_max_ctas(c);
+  if (G > cap) G = cap;
   if (G < 1) G = 1;
   return G;
 }

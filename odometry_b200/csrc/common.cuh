@@ -107,6 +107,8 @@ struct LmResult {        // per sequence, written by the solve kernel
   int n_res[ODO_MAX_LEVELS];
   float err[ODO_MAX_LEVELS];
   LmLevelOut last[ODO_MAX_LEVELS];
+  long long cyc_eval, cyc_reduce, cyc_step, cyc_total;  // SM clock cycles of CTA 0 (profiling aid)
+  long long cyc_dbg[4];
 };
 struct LmWork {          // device scratch of the solve kernel
   double* partials;      // [batch][2][G][32]
@@ -121,6 +123,7 @@ int launch_lm_solve(odo_ctx* c, const LmLists& L, const float* img2_pyr, int64_t
                     const odo_lm_params& p, const float* T_init_dev /*[batch][16]*/, LmResult* out_dev,
                     LmWork wk, int batch, int G, int only_level);
 size_t lm_work_bytes(const PyrGeom& g, int batch, int G);
+int lm_max_ctas(const odo_ctx* c);  // co-resident CTAs of the persistent solve kernel on this device
 void lm_work_bind(LmWork* w, void* mem, const PyrGeom& g, int batch, int G);
 
 // ---- depth.cu ------------------------------------------------------------------------------------

@@ -198,15 +198,21 @@ __device__ __forceinline__ void disparity_group(const int* __restrict__ gxy, int
     brx[i] = -1;
   }
   int rx = bnd + lane;
+  // one pointer per right row, advanced by 32 columns per iteration: every tap is an immediate offset
+  const float* q_pp = rpp + rx;
+  const float* q_p = rp + rx;
+  const float* q_c = rc + rx;
+  const float* q_n = rn + rx;
+  const float* q_nn = rnn + rx;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f, r7 = 0.f;
   if (rx < xg) {
-    r0 = rnn[rx]; r1 = rn[rx - 1]; r2 = rc[rx + 2]; r3 = rc[rx]; r4 = rc[rx - 2]; r5 = rp[rx + 1]; r6 = rp[rx - 1]; r7 = rpp[rx];
+    r0 = q_nn[0]; r1 = q_n[-1]; r2 = q_c[2]; r3 = q_c[0]; r4 = q_c[-2]; r5 = q_p[1]; r6 = q_p[-1]; r7 = q_pp[0];
   }
   while (rx < xg) {
     const int nx = rx + 32;
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f, n5 = 0.f, n6 = 0.f, n7 = 0.f;
     if (nx < xg) {
-      n0 = rnn[nx]; n1 = rn[nx - 1]; n2 = rc[nx + 2]; n3 = rc[nx]; n4 = rc[nx - 2]; n5 = rp[nx + 1]; n6 = rp[nx - 1]; n7 = rpp[nx];
+      n0 = q_nn[32]; n1 = q_n[31]; n2 = q_c[34]; n3 = q_c[32]; n4 = q_c[30]; n5 = q_p[33]; n6 = q_p[31]; n7 = q_pp[32];
     }
 #pragma unroll
     for (int i = 0; i < P; i++) {
@@ -221,6 +227,7 @@ __device__ __forceinline__ void disparity_group(const int* __restrict__ gxy, int
     }
     r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7;
     rx = nx;
+    q_pp += 32; q_p += 32; q_c += 32; q_n += 32; q_nn += 32;
   }
 #pragma unroll
   for (int i = 0; i < P; i++) {

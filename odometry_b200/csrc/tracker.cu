@@ -294,8 +294,8 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   t->npx = (int64_t)w * h;
   t->pyr_stride = (t->g.total + 3) / 4 * 4;
   // CTAs per sequence for the persistent LM kernel: fill the SMs across the batch
-  int G = c->sm_count / n_seq;
-  const int gmax = (int)((t->npx + 4095) / 4096);
+  int G = lm_max_ctas(c) / n_seq;
+  const int gmax = (int)((t->npx + 16383) / 16384);
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
   t->G_lm = G;
@@ -364,6 +364,17 @@ void odo_tracker_destroy(odo_tracker* t) {
   for (int i = 0; i <= ODO_N_STAGES; i++)
     if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   delete t;
+}
+
+// profiling aid (not in the public header): cycle split of the LM kernel for sequence 0 of the last step
+extern "C" int odo_tracker_lm_cycles(odo_tracker* t, long long out[8], int iters[8]) {
+  if (!t) return -1;
+  LmResult r;
+  if (cudaMemcpy(&r, t->res, sizeof(r), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  out[0] = r.cyc_eval; out[1] = r.cyc_reduce; out[2] = r.cyc_step; out[3] = r.cyc_total;
+  out[4] = r.cyc_dbg[0]; out[5] = r.cyc_dbg[1]; out[6] = r.cyc_dbg[2];
+  for (int i = 0; i < 8; i++) iters[i] = r.iters[i];
+  return 0;
 }
 
 int odo_tracker_stage_ms(const odo_tracker* t, float* ms_out) {
