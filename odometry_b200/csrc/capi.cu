@@ -4,8 +4,11 @@
 // the results; the batched tracker (tracker.cu) drives the same kernels with everything resident.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <vector>
+
+static std::atomic<uint64_t> g_pyr_id{1};
 
 static void* ctx_scratch(odo_ctx* c, int slot, size_t bytes) {
   if (c->scratch_bytes[slot] >= bytes && c->scratch[slot]) return c->scratch[slot];
@@ -94,6 +97,7 @@ void odo_ctx_destroy(odo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 16; i++)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
+  for (auto& e : c->pyr_pool) cudaFree(e.second);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -123,7 +127,15 @@ static int pyr_build(odo_ctx* c, const float* host, int w, int h, int levels, in
   odo_pyr* p = new odo_pyr();
   p->g = g;
   p->kind = kind;
-  if (cudaMalloc(&p->d, sizeof(float) * (size_t)g.total) != cudaSuccess) {
+  p->id = g_pyr_id.fetch_add(1);
+  const size_t pbytes = sizeof(float) * (size_t)g.total;
+  for (size_t i = 0; i < c->pyr_pool.size(); i++)
+    if (c->pyr_pool[i].first == pbytes) {
+      p->d = c->pyr_pool[i].second;
+      c->pyr_pool.erase(c->pyr_pool.begin() + i);
+      break;
+    }
+  if (!p->d && cudaMalloc(&p->d, pbytes) != cudaSuccess) {
     delete p;
     c->err = "cudaMalloc failed";
     return -1;
@@ -171,8 +183,12 @@ int odo_pyr_download(odo_ctx* c, const odo_pyr* p, int level, float* host_out) {
 
 void odo_pyr_release(odo_ctx* c, odo_pyr* p) {
   if (!p) return;
-  if (c) cudaStreamSynchronize(c->stream);
-  cudaFree(p->d);
+  if (c && c->pyr_pool.size() < 16) {
+    c->pyr_pool.emplace_back(sizeof(float) * (size_t)p->g.total, p->d);
+  } else {
+    if (c) cudaStreamSynchronize(c->stream);
+    cudaFree(p->d);
+  }
   delete p;
 }
 
@@ -204,6 +220,7 @@ static int lm_run(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_py
   const PyrGeom& g = i1->g;
   LmLists L;
   const size_t lbytes = lm_lists_bytes(g, 1, &L);
+  const bool lists_realloc = !(c->scratch[SLOT_LISTS] && c->scratch_bytes[SLOT_LISTS] >= lbytes);
   void* lmem = ctx_scratch(c, SLOT_LISTS, lbytes);
   if (!lmem) return -1;
   lm_lists_bind(&L, lmem, g, 1);
@@ -218,7 +235,14 @@ static int lm_run(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_py
   LmResult* res_dev = (LmResult*)(io + 256);
   ODO_CUDA_OK(c, cudaMemcpyAsync(T_dev, T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(res_dev, 0, sizeof(LmResult), c->stream));
-  launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr);
+  const bool lists_cached = !lists_realloc && c->lists_img_id == i1->id && c->lists_dep_id == d1->id &&
+                            c->lists_K.fx == p->K.fx && c->lists_K.cx == p->K.cx && c->lists_K.cy == p->K.cy;
+  if (!lists_cached) {
+    launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr);
+    c->lists_img_id = i1->id;
+    c->lists_dep_id = d1->id;
+    c->lists_K = p->K;
+  }
   if (launch_lm_solve(c, L, i2->d, 0, g, *p, T_dev, res_dev, wk, 1, G, only_level) != 0) return -1;
   ODO_CUDA_OK(c, cudaMemcpyAsync(host_res, res_dev, sizeof(LmResult), cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));

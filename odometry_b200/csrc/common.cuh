@@ -6,6 +6,8 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/odo_b200.h"
 
@@ -20,6 +22,13 @@ struct odo_ctx {
   // scratch cache for the single-call entry points (grown on demand, freed with the context)
   void* scratch[16] = {nullptr};
   size_t scratch_bytes[16] = {0};
+  // the LM point lists in scratch were built from this (image, inverse-depth) pyramid pair: a caller that
+  // solves several frames against one keyframe (run_odometry_kitti_offline.cpp:215) pays for them once
+  uint64_t lists_img_id = 0, lists_dep_id = 0;
+  odo_intrinsics lists_K = {0.f, 0.f, 0.f};
+  // released pyramid buffers, reused by the next build of the same size (all work of a context is
+  // ordered on its one stream, so reuse needs no synchronisation and no cudaMalloc per frame)
+  std::vector<std::pair<size_t, float*>> pyr_pool;
 };
 
 #define ODO_CUDA_OK(ctx, expr)                                                              \
@@ -60,6 +69,7 @@ struct odo_pyr {
   PyrGeom g;
   float* d = nullptr;  // device, packed levels
   int kind = 0;        // 0 image, 1 inverse depth
+  uint64_t id = 0;     // unique per build (never reused), keys the context's point-list cache
 };
 
 // ---- pyramid.cu ----------------------------------------------------------------------------------
