@@ -102,14 +102,15 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
 
-def render_sequences(n_seq, n_frames, seq_offset, device):
-    """u8 frames [n_frames][n_seq][2][H][W] on `device` (torch), sequence ids seq_offset..+n_seq."""
+def render_sequences(seq_ids, n_frames, device):
+    """u8 frames [n_frames][len(seq_ids)][2][H][W] on `device` (torch) of the given global sequence ids."""
     import torch
     from odometry_b200 import synth
+    n_seq = len(seq_ids)
     out = torch.empty((n_frames, n_seq, 2, H, W), dtype=torch.uint8, device=device)
     poses = synth.trajectory(n_frames, step=0.8)
-    for s in range(n_seq):
-        sc = synth.make_scene(seq_offset + s, n_frames, 0.8)
+    for s, sid in enumerate(seq_ids):
+        sc = synth.make_scene(sid, n_frames, 0.8)
         for f, T in enumerate(poses):
             L, R, _ = synth.render_stereo(sc, T, W, H, device)
             out[f, s, 0], out[f, s, 1] = L, R
@@ -154,7 +155,7 @@ def run_reference(args, rank, world):
     n_seq = max(1, min(cores, 32))
     n_frames = 1 + args.warmup + args.steps
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    frames = render_sequences(n_seq, n_frames, 0, dev).cpu().numpy()
+    frames = render_sequences(list(range(n_seq)), n_frames, dev).cpu().numpy()
     import oracle
     oracle.lib()
     # warm-up steps are part of the same trajectory: time only the last `steps` frames
@@ -201,7 +202,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from odometry_b200 import capi
+    from odometry_b200 import capi, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
@@ -212,22 +213,17 @@ def main():
 
     S, K, Wm = args.seqs, args.steps, args.warmup
     n_frames = 1 + Wm + K
-    frames_u8 = render_sequences(S, n_frames, rank * S, dev)           # [F][S][2][H][W] u8 on device
+    # config 4: world*S independent sequences, sequence s on rank s mod world (odometry_b200/shard.py)
+    seq_ids = shard.shard_sequences(world * S, world, rank)
+    frames_u8 = render_sequences(seq_ids, n_frames, dev)                # [F][S][2][H][W] u8 on device
     stream = torch.cuda.current_stream(dev)
     ctx = capi.Context(local_rank, stream.cuda_stream)
 
     def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        shard.barrier(dev)
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(ms, dev)
 
     # ---------------- leg 1: inputs resident in HBM ----------------
     frames_f32 = frames_u8.to(torch.float32)                            # [F][S][2][H][W] float32 on device

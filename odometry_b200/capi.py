@@ -222,7 +222,9 @@ class Context:
         rc = lib().odo_select_pixels(self.h, _p(L), _p(R), w, h, C.byref(p), _p(bl), _p(br), _p(val, C.c_uint8))
         return rc, bl, br, val
 
-    def disparity_search(self, bl, br, val, p: DepthParams):
+    def disparity_search(self, bl, br, val, p: DepthParams, want_ssd=True):
+        """want_ssd=False: min_ssd is not requested (returned as zeros), which lets the library use its
+        exact integer path when both images are multiples of 1/16."""
         bl, br = _f32(bl), _f32(br)
         h, w = bl.shape
         val = np.ascontiguousarray(val, np.uint8)
@@ -231,7 +233,7 @@ class Context:
         match = np.zeros((h, w), np.int32)
         ssd = np.zeros((h, w), np.float32)
         rc = lib().odo_disparity_search(self.h, _p(bl), _p(br), w, h, C.byref(p), _p(val, C.c_uint8), _p(disp),
-                                        _p(dep), _p(match, C.c_int32), _p(ssd))
+                                        _p(dep), _p(match, C.c_int32), _p(ssd) if want_ssd else None)
         return rc, disp, dep, match, ssd
 
     def depth_optimize(self, L, R, dep, val, p: DepthParams):

@@ -152,7 +152,12 @@ struct DepthWork {
   int cap;             // pixel-list capacity per sequence
   int64_t blurL_stride;  // elements between sequences in blurL (the tracker aliases level 0 of the image pyramid)
   int64_t dep_stride;    // elements between sequences in dep (the tracker aliases level 0 of the depth pyramid)
-  int n_items;         // disparity work items (lists of <= 80 pixels) per sequence; 512 in the pipeline
+  // exact integer path of the line search (depth.cu, k_quantize): q = 16 * blur as u16, pattern energy of
+  // every right candidate, and per sequence "both blurred images are multiples of 1/16 in [0, 255]"
+  uint16_t* qL;        // [batch][w*h]
+  uint16_t* qR;
+  int* eR;             // [batch][w*h]
+  int* exact;          // [batch]
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)

@@ -136,203 +136,298 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
 }
 
 // ---- disparity line search ----------------------------------------------------------------------------
-// Work item = one list of <= 80 selected pixels in raster order (in the pipeline: one block of the
-// 16x32 selection grid).  The CTA stages the right rows its pixels need in shared memory (in chunks of
-// kRowsPerChunk image rows), then each warp takes a group of up to kDispP pixels of the SAME image row:
-// every lane loads the 8 right taps of its candidate column once and evaluates the SSD against the
-// kDispP left patterns held in registers, so the shared-memory traffic per candidate drops by kDispP
-// and the loop is bound by the 23 fp32 operations per candidate that the reference's association
-// requires (no FMA, fixed tree).
-constexpr int kDispThreads = 256;
+// Work item = one image row of one sequence.  The CTA compacts the row of the validity mask into an
+// ascending list of selected columns, stages the five right rows y-2..y+2 it needs in shared memory
+// once, and its warps take groups of four consecutive selected pixels: lane `j` evaluates candidate
+// columns boundary + j + 32k, loads the 8 right taps once (shared-memory loads at compile-time offsets:
+// the row pitch is a template parameter) and scores them against the four left patterns held in
+// registers.  Per-lane strict '<' in ascending order plus a warp-shuffle argmin with "smaller column wins
+// ties" reproduces the reference's first-minimum rule (src/depth_estimate.cpp:382-386).
+//
+// Two arithmetic paths, selected per sequence:
+//  * fp32 (QPATH = false): sub, mul and the add tree in exactly the association of the reference's AVX
+//    hadd sequence (ComputeSsdPattern8Sse, :435-453), no FMA.  Exact for arbitrary float input.
+//  * integer (QPATH = true): when both blurred images hold only multiples of 1/16 in [0, 255] -- always
+//    the case for u8-sourced frames (imread -> convertTo, run_odometry_kitti_offline.cpp:342-348): the
+//    3x3 [1 2 1]^2/16 blur of integers -- every tap difference is a multiple of 1/16, its square a
+//    multiple of 1/256 below 2^16, and every fp32 partial sum below 2^16 is EXACT in any association.
+//    Rounding can therefore touch only costs >= 2^16, which (rounding being monotone) stay >= 2^16 and
+//    are rejected by ssd_th < 2^16.  So with q = 16 * blur (12-bit integers) the reference's argmin and
+//    accept test are reproduced bit for bit by integer arithmetic on 256*SSD = El + Er - 2*cross:
+//    El / Er are the pattern energies of the left pixel / right candidate, cross the 8-tap correlation.
+//    Per (pixel, candidate) that is 8 IMAD + compare/select instead of 8 FSUB + 8 FMUL + 7 FADD +
+//    compare/select, and Er is shared by the pixels of a group.  k_quantize builds q for both images,
+//    Er for the right one, and clears `exact` on any other value; such sequences take the fp32 path.
+constexpr int kDispThreads = 128;
 constexpr int kDispWarps = kDispThreads / 32;
 constexpr int kDispP = 4;
-constexpr int kRowsPerChunk = 4;
-constexpr int kStagedRows = kRowsPerChunk + 4;
-constexpr int kDispStage = 0;
 
-__device__ __forceinline__ float ssd8(float l0, float l1, float l2, float l3, float l4, float l5, float l6, float l7,
-                                      float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7) {
+__host__ __device__ inline int q_pitch(int W) { return (W + 7) & ~7; }  // q / Er planes: 16-byte aligned rows
+
+__global__ void __launch_bounds__(256) k_quantize(int W, int H, DepthWork d) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int64_t npx = (int64_t)W * H;
+  const int QP = q_pitch(W);
+  const int64_t qpx = (int64_t)QP * H;
+  const float* bl = d.blurL + b * d.blurL_stride;
+  const float* br = d.blurR + b * npx;
+  bool bad = false;
+  if (x < W && y < H) {
+    const int64_t o = (int64_t)y * W + x;
+    const int64_t qo = b * qpx + (int64_t)y * QP + x;
+    const float l16 = __fmul_rn(__ldg(bl + o), 16.0f), r16 = __fmul_rn(__ldg(br + o), 16.0f);
+    bad = !(l16 >= 0.0f && l16 <= 4080.0f && l16 == rintf(l16) && r16 >= 0.0f && r16 <= 4080.0f && r16 == rintf(r16));
+    d.qL[qo] = (uint16_t)(bad ? 0 : (int)l16);
+    d.qR[qo] = (uint16_t)(bad ? 0 : (int)r16);
+    int e = 0;
+    if (x >= 2 && x < W - 2 && y >= 2 && y < H - 2) {
+      // pattern taps (:380-381): nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x]
+      const float t[8] = {__ldg(br + o + 2 * W), __ldg(br + o + W - 1), __ldg(br + o + 2), __ldg(br + o), __ldg(br + o - 2),
+                          __ldg(br + o - W + 1), __ldg(br + o - W - 1), __ldg(br + o - 2 * W)};
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int q = (int)__fmul_rn(t[k], 16.0f);  // garbage when not exact: the flag sends the search elsewhere
+        e += q * q;
+      }
+    }
+    d.eR[qo] = e;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&d.exact[b], 0);
+}
+
+__device__ __forceinline__ float ssd8(const float* l, float r0, float r1, float r2, float r3, float r4, float r5,
+                                      float r6, float r7) {
   // ComputeSsdPattern8Sse (:435-453): sub, mul, hadd, hadd, movehl + add
-  float d0 = __fsub_rn(l0, r0), d1 = __fsub_rn(l1, r1), d2 = __fsub_rn(l2, r2), d3 = __fsub_rn(l3, r3),
-        d4 = __fsub_rn(l4, r4), d5 = __fsub_rn(l5, r5), d6 = __fsub_rn(l6, r6), d7 = __fsub_rn(l7, r7);
+  float d0 = __fsub_rn(l[0], r0), d1 = __fsub_rn(l[1], r1), d2 = __fsub_rn(l[2], r2), d3 = __fsub_rn(l[3], r3),
+        d4 = __fsub_rn(l[4], r4), d5 = __fsub_rn(l[5], r5), d6 = __fsub_rn(l[6], r6), d7 = __fsub_rn(l[7], r7);
   d0 = __fmul_rn(d0, d0); d1 = __fmul_rn(d1, d1); d2 = __fmul_rn(d2, d2); d3 = __fmul_rn(d3, d3);
   d4 = __fmul_rn(d4, d4); d5 = __fmul_rn(d5, d5); d6 = __fmul_rn(d6, d6); d7 = __fmul_rn(d7, d7);
   return __fadd_rn(__fadd_rn(__fadd_rn(d0, d1), __fadd_rn(d2, d3)), __fadd_rn(__fadd_rn(d4, d5), __fadd_rn(d6, d7)));
 }
 
-// One warp, one group of P pixels of image row y (P is a template parameter so that a short group does
-// not pay for absent pixels).  Lane `lane` evaluates candidate columns boundary + lane, + 32, ...; the
-// taps of the next column are fetched while the current one is evaluated.
-template <int P>
-__device__ __forceinline__ void disparity_group(const int* __restrict__ gxy, int y, int W, int bnd, int lane,
-                                                const float* __restrict__ bl, const float* __restrict__ rpp,
-                                                int rpitch, const odo_depth_params& p, const DepthWork& d,
-                                                int64_t img_off, int b) {
-  int xs[P];
-  float l[P][8];
-  int xg = 0;
-#pragma unroll
-  for (int i = 0; i < P; i++) {
-    const int x = gxy[i] & 0xffff;
-    xs[i] = x;
-    xg = max(xg, x);
-    // left pattern, _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
-    l[i][0] = __ldg(bl + (int64_t)(y + 2) * W + x);
-    l[i][1] = __ldg(bl + (int64_t)(y + 1) * W + x - 1);
-    l[i][2] = __ldg(bl + (int64_t)y * W + x + 2);
-    l[i][3] = __ldg(bl + (int64_t)y * W + x);
-    l[i][4] = __ldg(bl + (int64_t)y * W + x - 2);
-    l[i][5] = __ldg(bl + (int64_t)(y - 1) * W + x + 1);
-    l[i][6] = __ldg(bl + (int64_t)(y - 1) * W + x - 1);
-    l[i][7] = __ldg(bl + (int64_t)(y - 2) * W + x);
-  }
-  const float* rp = rpp + rpitch;
-  const float* rc = rp + rpitch;
-  const float* rn = rc + rpitch;
-  const float* rnn = rn + rpitch;
-  float best[P];
-  int brx[P];
-#pragma unroll
-  for (int i = 0; i < P; i++) {
-    best[i] = 1e+10f;
-    brx[i] = -1;
-  }
-  int rx = bnd + lane;
-  // one pointer per right row, advanced by 32 columns per iteration: every tap is an immediate offset
-  const float* q_pp = rpp + rx;
-  const float* q_p = rp + rx;
-  const float* q_c = rc + rx;
-  const float* q_n = rn + rx;
-  const float* q_nn = rnn + rx;
-  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f, r7 = 0.f;
-  if (rx < xg) {
-    r0 = q_nn[0]; r1 = q_n[-1]; r2 = q_c[2]; r3 = q_c[0]; r4 = q_c[-2]; r5 = q_p[1]; r6 = q_p[-1]; r7 = q_pp[0];
-  }
-  while (rx < xg) {
-    const int nx = rx + 32;
-    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f, n4 = 0.f, n5 = 0.f, n6 = 0.f, n7 = 0.f;
-    if (nx < xg) {
-      n0 = q_nn[32]; n1 = q_n[31]; n2 = q_c[34]; n3 = q_c[32]; n4 = q_c[30]; n5 = q_p[33]; n6 = q_p[31]; n7 = q_pp[32];
-    }
-#pragma unroll
-    for (int i = 0; i < P; i++) {
-      const float ssd = ssd8(l[i][0], l[i][1], l[i][2], l[i][3], l[i][4], l[i][5], l[i][6], l[i][7], r0, r1, r2, r3,
-                             r4, r5, r6, r7);
-      // candidates of pixel i are right_x = boundary .. x_i - 1; strict '<' in ascending rx keeps
-      // the FIRST minimum (:382-386)
-      if (rx < xs[i] && ssd < best[i]) {
-        best[i] = ssd;
-        brx[i] = rx;
-      }
-    }
-    r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7;
-    rx = nx;
-    q_pp += 32; q_p += 32; q_c += 32; q_n += 32; q_nn += 32;
-  }
-#pragma unroll
-  for (int i = 0; i < P; i++) {
-    // warp argmin: smaller cost, ties to the smaller column
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
-      const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
-      const bool take = (orx >= 0) && (brx[i] < 0 || ob < best[i] || (ob == best[i] && orx < brx[i]));
-      if (take) {
-        best[i] = ob;
-        brx[i] = orx;
-      }
-    }
-    if (lane == i) {
-      const int x = xs[i];
-      const int64_t o = img_off + (int64_t)y * W + x;
-      if (d.min_ssd) d.min_ssd[o] = best[i];
-      if (!(best[i] > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
-        const float disp = (float)abs(x - brx[i]);
-        if (d.disp) d.disp[o] = disp;
-        d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
-        if (d.match_x) d.match_x[o] = brx[i];
-        atomicAdd(&d.stats[b].n_matched, 1);
-      }
-    }
-  }
-}
+template <bool QPATH> struct DispTraits;
+template <> struct DispTraits<true> {
+  typedef uint16_t elem;   // staged right rows: q = 16 * blur
+  typedef int acc;         // 2*cross - Er, maximised
+};
+template <> struct DispTraits<false> {
+  typedef float elem;      // staged right rows: the blurred image itself
+  typedef float acc;       // SSD, minimised
+};
 
-__global__ void __launch_bounds__(kDispThreads, 3) k_disparity(int W, int H, odo_depth_params p, DepthWork d) {
-  extern __shared__ float s_rows[];  // [kStagedRows][pitch] right rows y0-2 .. y1+2 of the current chunk
-  __shared__ int s_xy[kSelMax];
-  __shared__ int s_g[kSelMax + 1];   // group start indices
-  __shared__ int s_ng, s_xmax;
-  const int b = blockIdx.y, item = blockIdx.x;
-  const int cnt = d.sel_count[(int64_t)b * d.n_items + item];
-  if (cnt <= 0) return;
-  const int* list = d.sel_xy + ((int64_t)b * d.n_items + item) * kSelMax;
-  const int64_t npx = (int64_t)W * H;
+// PITCH: shared-memory row pitch in elements (W + 12 <= PITCH: 2 guard columns + 16-byte staging); staged column c of image row r lives at
+// rows[r * PITCH + c + 2] so that the taps at c - 2 of the first candidate stay inside the row.
+template <bool QPATH, int PITCH>
+__global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W, int H, odo_depth_params p, DepthWork d,
+                                                                          int q_eligible) {
+  typedef typename DispTraits<QPATH>::elem elem_t;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  elem_t* s_rows = reinterpret_cast<elem_t*>(s_raw);                       // [5][PITCH]
+  int* s_er = reinterpret_cast<int*>(s_raw + sizeof(elem_t) * 5 * PITCH);   // [PITCH]   (QPATH only)
+  uint16_t* s_xs = reinterpret_cast<uint16_t*>(s_raw + sizeof(elem_t) * 5 * PITCH + (QPATH ? sizeof(int) * PITCH : 0));
+  __shared__ int s_w[kDispWarps];
+  const int b = blockIdx.y;
+  const bool fast = q_eligible && d.exact[b] != 0;
+  if (fast != QPATH) return;
   const int bnd = p.boundary;
-  if (threadIdx.x < cnt) s_xy[threadIdx.x] = list[threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // groups of <= kDispP consecutive list entries that share an image row
-    int ng = 0, run = 0, ycur = -1, xmax = 0;
-    for (int k = 0; k < cnt; k++) {
-      const int y = s_xy[k] >> 16, x = s_xy[k] & 0xffff;
-      xmax = max(xmax, x);
-      if (y != ycur || run == kDispP) {
-        s_g[ng++] = k;
-        run = 0;
-        ycur = y;
-      }
-      run++;
+  const int y = bnd + blockIdx.x;
+  const int64_t npx = (int64_t)W * H;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  // ---- selected columns of this row, ascending: "if (*(left_val_row_ptr+x) == 0) continue", :352 ----
+  const uint8_t* vrow = d.val + b * npx + (int64_t)y * W;
+  int n = 0;
+  for (int x0 = bnd; x0 < W - bnd; x0 += kDispThreads) {
+    const int x = x0 + threadIdx.x;
+    const bool f = (x < W - bnd) && (__ldg(vrow + x) != 0);
+    const unsigned mk = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_w[wid] = __popc(mk);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kDispWarps; k++) {
+      if (k < wid) woff += s_w[k];
+      tot += s_w[k];
     }
-    s_g[ng] = cnt;
-    s_ng = ng;
-    s_xmax = xmax;
+    if (f) s_xs[n + woff + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)x;
+    n += tot;
+    __syncthreads();
+  }
+  if (n == 0) return;
+  const int xlast = s_xs[n - 1];
+
+  // ---- stage right rows y-2 .. y+2, columns [0, xlast + 3) (candidates end at xlast - 1, taps reach +2) ----
+  const int ncol = min(xlast + 3, W);
+  if (QPATH) {
+    const int QP = q_pitch(W);
+    const int64_t qpx = (int64_t)QP * H;
+    const uint16_t* src = d.qR + b * qpx + (int64_t)(y - 2) * QP;
+    const int nv = (ncol + 7) >> 3;  // 8 u16 per 16-byte load; plane rows are padded to a multiple of 8
+    for (int i = threadIdx.x; i < 5 * nv; i += kDispThreads) {
+      const int r = i / nv, v = i - r * nv;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * QP) + v);
+      // destination columns are shifted by 2 elements: 4-byte aligned stores
+      uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(s_rows) + r * PITCH + 2 + v * 8);
+      dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+    }
+    const int* esrc = d.eR + b * qpx + (int64_t)y * QP;
+    const int ne4 = (ncol + 3) >> 2;
+    for (int i = threadIdx.x; i < ne4; i += kDispThreads)
+      reinterpret_cast<int4*>(s_er)[i] = __ldg(reinterpret_cast<const int4*>(esrc) + i);
+  } else {
+    const float* src = d.blurR + b * npx + (int64_t)(y - 2) * W;
+    for (int r = 0; r < 5; r++)
+      for (int i = threadIdx.x; i < ncol; i += kDispThreads)
+        reinterpret_cast<float*>(s_rows)[r * PITCH + 2 + i] = __ldg(src + (int64_t)r * W + i);
   }
   __syncthreads();
-  const int ng = s_ng;
-  const int ymin = s_xy[0] >> 16, ymax = s_xy[cnt - 1] >> 16;
-  const int pitch = W + 4;
-  const int ncol = min(s_xmax + 3, W);  // candidates end at xmax-1, taps reach +2
-  const float* br = d.blurR + b * npx;
-  const float* bl = d.blurL + b * d.blurL_stride;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // kDispStage == 0: the right taps are read straight from global memory; the five rows a group needs
-  // (<= 25 KB) are shared by every group of that image row on the SM and stay L1-resident.
-  // kDispStage == 1: the rows of each chunk of kRowsPerChunk image rows are staged in shared memory.
-  for (int y0 = ymin; y0 <= ymax; y0 += kRowsPerChunk) {
-    const int y1 = min(y0 + kRowsPerChunk - 1, ymax);
-    if (kDispStage) {
-      // skip chunks without pixels (lists of the test hook may be sparse in y)
-      bool any = false;
-      for (int g = 0; g < ng && !any; g++) {
-        const int y = s_xy[s_g[g]] >> 16;
-        any = (y >= y0 && y <= y1);
-      }
-      if (!any) continue;
-      __syncthreads();
-      const int nrows = y1 - y0 + 5;
-      for (int r = 0; r < nrows; r++) {
-        const int yy = y0 - 2 + r;
-        if (yy < 0 || yy >= H) continue;
-        const float* src = br + (int64_t)yy * W;
-        float* dst = s_rows + r * pitch;
-        for (int i = threadIdx.x; i < ncol; i += kDispThreads) dst[i] = __ldg(src + i);
-      }
-      __syncthreads();
-    } else if (y0 != ymin) {
-      break;  // one pass over all groups is enough without staging
+
+  const int ng = (n + kDispP - 1) / kDispP;
+  for (int g0 = 0; g0 < ng; g0 += kDispWarps) {
+    // snake order over the rounds: later groups have more candidates, alternate which warp gets them
+    const int g = g0 + (((g0 / kDispWarps) & 1) ? (kDispWarps - 1 - wid) : wid);
+    if (g >= ng) continue;
+    int xs[kDispP];
+    int xg = 0, xmin = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kDispP; i++) {
+      const int k = g * kDispP + i;
+      xs[i] = (k < n) ? (int)s_xs[k] : 0;  // 0: an absent pixel has no candidates (rx >= boundary > 0)
+      xg = max(xg, xs[i]);
+      if (k < n) xmin = min(xmin, xs[i]);
     }
-    for (int g = wid; g < ng; g += kDispWarps) {
-      const int k0 = s_g[g], n = s_g[g + 1] - k0;
-      const int y = s_xy[k0] >> 16;
-      if (kDispStage && (y < y0 || y > y1)) continue;
-      const int rpitch = kDispStage ? pitch : W;
-      const float* rpp = kDispStage ? s_rows + (y - y0) * pitch : br + (int64_t)(y - 2) * W;
-      const int64_t img_off = b * npx;  // disp / match_x / min_ssd planes
-      switch (n) {
-        case 1: disparity_group<1>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
-        case 2: disparity_group<2>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
-        case 3: disparity_group<3>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
-        default: disparity_group<4>(s_xy + k0, y, W, bnd, lane, bl, rpp, rpitch, p, d, img_off, b); break;
+    int brx[kDispP];
+#pragma unroll
+    for (int i = 0; i < kDispP; i++) brx[i] = -1;
+    int rx = bnd + lane;
+
+    if (QPATH) {
+      const int QP = q_pitch(W);
+      const uint16_t* lq = d.qL + b * (int64_t)QP * H + (int64_t)y * QP;
+      int l2[kDispP][8], El[kDispP], best[kDispP];
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+        const uint16_t* c = lq + max(xs[i], 2);
+        const int t[8] = {c[2 * QP], c[QP - 1], c[2], c[0], c[-2], c[-QP + 1], c[-QP - 1], c[-2 * QP]};
+        int e = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          e += t[k] * t[k];
+          l2[i][k] = 2 * t[k];
+        }
+        El[i] = e;
+        best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
+      }
+      const uint16_t* q_c = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2 + rx;
+      const int* q_e = s_er + rx;
+      // candidates below the smallest x of the group are candidates of every pixel: no range test
+      for (; rx < xmin; rx += 32, q_c += 32, q_e += 32) {
+        const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                  r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+        const int ne = -q_e[0];
+#pragma unroll
+        for (int i = 0; i < kDispP; i++) {
+          int acc = ne + l2[i][0] * r0;
+          acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
+          acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+          if (acc > best[i]) {  // strict, ascending rx: the FIRST minimum stays (:382-386)
+            best[i] = acc;
+            brx[i] = rx;
+          }
+        }
+      }
+      for (; rx < xg; rx += 32, q_c += 32, q_e += 32) {
+        const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                  r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+        const int ne = -q_e[0];
+#pragma unroll
+        for (int i = 0; i < kDispP; i++) {
+          int acc = ne + l2[i][0] * r0;
+          acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
+          acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+          if (rx < xs[i] && acc > best[i]) {
+            best[i] = acc;
+            brx[i] = rx;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+        int ssd = El[i] - best[i];  // 256 * SSD, exact
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const int ob = __shfl_xor_sync(0xffffffffu, ssd, o);
+          const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
+          const bool take = (orx >= 0) && (brx[i] < 0 || ob < ssd || (ob == ssd && orx < brx[i]));
+          if (take) {
+            ssd = ob;
+            brx[i] = orx;
+          }
+        }
+        if (lane == i && g * kDispP + i < n && brx[i] >= 0) {  // absent pixels of a short group took part in phase A
+          const int x = xs[i];
+          const int64_t o = b * npx + (int64_t)y * W + x;
+          // exact in fp32 below 2^24; anything larger is far above ssd_th (< 2^16) whatever its rounding
+          const float fssd = __fmul_rn((float)ssd, 1.0f / 256.0f);
+          if (!(fssd > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+            const float disp = (float)abs(x - brx[i]);
+            if (d.disp) d.disp[o] = disp;
+            d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+            if (d.match_x) d.match_x[o] = brx[i];
+            atomicAdd(&d.stats[b].n_matched, 1);
+          }
+        }
+      }
+    } else {
+      const float* lf = d.blurL + b * d.blurL_stride + (int64_t)y * W;
+      float l[kDispP][8], best[kDispP];
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+        const float* c = lf + max(xs[i], 2);
+        // _mm256_set_ps lanes 0..7 = nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x] (:380-381)
+        l[i][0] = __ldg(c + 2 * W); l[i][1] = __ldg(c + W - 1); l[i][2] = __ldg(c + 2); l[i][3] = __ldg(c);
+        l[i][4] = __ldg(c - 2); l[i][5] = __ldg(c - W + 1); l[i][6] = __ldg(c - W - 1); l[i][7] = __ldg(c - 2 * W);
+        best[i] = 1e+10f;
+      }
+      const float* q_c = reinterpret_cast<const float*>(s_rows) + 2 * PITCH + 2 + rx;
+      for (; rx < xg; rx += 32, q_c += 32) {
+        const float r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                    r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+#pragma unroll
+        for (int i = 0; i < kDispP; i++) {
+          const float ssd = ssd8(l[i], r0, r1, r2, r3, r4, r5, r6, r7);
+          if (rx < xs[i] && ssd < best[i]) {
+            best[i] = ssd;
+            brx[i] = rx;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kDispP; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+          const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
+          const bool take = (orx >= 0) && (brx[i] < 0 || ob < best[i] || (ob == best[i] && orx < brx[i]));
+          if (take) {
+            best[i] = ob;
+            brx[i] = orx;
+          }
+        }
+        if (lane == i && g * kDispP + i < n) {
+          const int x = xs[i];
+          const int64_t o = b * npx + (int64_t)y * W + x;
+          if (d.min_ssd) d.min_ssd[o] = best[i];
+          if (!(best[i] > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+            const float disp = (float)abs(x - brx[i]);
+            if (d.disp) d.disp[o] = disp;
+            d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+            if (d.match_x) d.match_x[o] = brx[i];
+            atomicAdd(&d.stats[b].n_matched, 1);
+          }
+        }
       }
     }
   }
@@ -525,6 +620,8 @@ size_t depth_work_bytes(int w, int h, int batch, bool debug) {
   bytes += al((size_t)batch * kGridBlocks * 4);                 // sel_count
   bytes += al((size_t)batch * sizeof(odo_depth_stats));
   bytes += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);   // refinement state
+  const size_t qpx = (size_t)q_pitch(w) * h * batch + 16;  // +16: the staging reads whole 16-byte vectors
+  bytes += al(qpx * 2) * 2 + al(qpx * 4) + al((size_t)batch * 4);  // qL, qR, eR, exact
   return bytes;
 }
 
@@ -548,9 +645,13 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->sel_xy = (int*)p; p += al((size_t)batch * kGridBlocks * kSelMax * 4);
   d->sel_count = (int*)p; p += al((size_t)batch * kGridBlocks * 4);
   d->stats = (odo_depth_stats*)p; p += al((size_t)batch * sizeof(odo_depth_stats));
-  d->ref_state = (float*)p;
+  d->ref_state = (float*)p; p += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);
+  const size_t qpx = (size_t)q_pitch(w) * h * batch + 16;
+  d->qL = (uint16_t*)p; p += al(qpx * 2);
+  d->qR = (uint16_t*)p; p += al(qpx * 2);
+  d->eR = (int*)p; p += al(qpx * 4);
+  d->exact = (int*)p;
   d->cap = kGridBlocks * kSelMax;
-  d->n_items = kGridBlocks;
   d->blurL_stride = (int64_t)w * h;
   d->dep_stride = (int64_t)w * h;
 }
@@ -572,16 +673,43 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
   c->launches++;
 }
 
-void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
-  if (d.n_items <= 0) return;
-  const size_t smem = kDispStage ? sizeof(float) * kStagedRows * (size_t)(w + 4) : 0;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    cudaFuncSetAttribute(k_disparity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = smem;
+template <bool QPATH, int PITCH>
+static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params& p, const DepthWork& d, int batch,
+                               int q_eligible) {
+  const size_t esz = QPATH ? sizeof(uint16_t) : sizeof(float);
+  const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH : 0) + sizeof(uint16_t) * PITCH;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_disparity<QPATH, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
   }
-  k_disparity<<<dim3(d.n_items, batch), kDispThreads, smem, c->stream>>>(w, h, p, d);
+  k_disparity<QPATH, PITCH><<<dim3(h - 2 * p.boundary, batch), kDispThreads, smem, c->stream>>>(w, h, p, d, q_eligible);
   c->launches++;
+}
+
+void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
+  if (h - 2 * p.boundary <= 0 || p.boundary < 2) return;
+  // exact integer path (see k_quantize); min_ssd (a test-hook output) is defined by the fp32 path
+  const int q_eligible = (d.qL && !d.min_ssd && p.ssd_th < 65536.0f) ? 1 : 0;
+  if (q_eligible) {
+    cudaMemsetAsync(d.exact, 0xff, sizeof(int) * batch, c->stream);
+    dim3 grid((w + 31) / 32, (h + 7) / 8, batch), block(32, 8);
+    k_quantize<<<grid, block, 0, c->stream>>>(w, h, d);
+    c->launches++;
+  }
+  // both arithmetic paths are launched; a sequence is served by exactly one of them (its `exact` flag)
+  if (w + 12 <= 1280) {
+    if (q_eligible) launch_disparity_t<true, 1280>(c, w, h, p, d, batch, 1);
+    launch_disparity_t<false, 1280>(c, w, h, p, d, batch, q_eligible);
+  } else if (w + 12 <= 2048) {
+    if (q_eligible) launch_disparity_t<true, 2048>(c, w, h, p, d, batch, 1);
+    launch_disparity_t<false, 2048>(c, w, h, p, d, batch, q_eligible);
+  } else if (w + 12 <= 4096) {
+    if (q_eligible) launch_disparity_t<true, 4096>(c, w, h, p, d, batch, 1);
+    launch_disparity_t<false, 4096>(c, w, h, p, d, batch, q_eligible);
+  } else {
+    c->err = "disparity search: images wider than 4084 pixels are not supported";
+  }
 }
 
 // scratch for the refinement's group reduction lives behind the refinement state

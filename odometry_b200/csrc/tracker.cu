@@ -484,37 +484,11 @@ int odo_disparity_search(odo_ctx* c, const float* blur_left, const float* blur_r
   ODO_CUDA_OK(c, cudaMemsetAsync(dw.disp, 0, npx * 4, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(dw.dep, 0, npx * 4, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(dw.match_x, 0xff, npx * 4, c->stream));
-  ODO_CUDA_OK(c, cudaMemsetAsync(dw.min_ssd, 0, npx * 4, c->stream));
+  if (!min_ssd) dw.min_ssd = nullptr;  // costs not requested: the exact integer path may serve the call
+  else ODO_CUDA_OK(c, cudaMemsetAsync(dw.min_ssd, 0, npx * 4, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(dw.stats, 0, sizeof(odo_depth_stats), c->stream));
-  // work items for an arbitrary caller-provided mask: every pixel the reference's loops visit
-  // (y, x in [boundary, size - boundary), val != 0, :346-354) in raster order, 80 per item
-  std::vector<int> items, counts;
-  {
-    int fill = 80;
-    for (int y = p->boundary; y < h - p->boundary; y++)
-      for (int x = p->boundary; x < w - p->boundary; x++)
-        if (val[(size_t)y * w + x] != 0) {
-          if (fill == 80) {
-            items.resize(items.size() + 80, -1);
-            counts.push_back(0);
-            fill = 0;
-          }
-          items[items.size() - 80 + fill] = (y << 16) | x;
-          counts.back() = ++fill;
-        }
-  }
-  if (!counts.empty()) {
-    int* li = (int*)scratch(c, 12, items.size() * sizeof(int) + counts.size() * sizeof(int));
-    if (!li) return -1;
-    int* lc = li + items.size();
-    ODO_CUDA_OK(c, cudaMemcpyAsync(li, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    ODO_CUDA_OK(c, cudaMemcpyAsync(lc, counts.data(), counts.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    dw.sel_xy = li;
-    dw.sel_count = lc;
-    dw.n_items = (int)counts.size();
-    launch_disparity(c, w, h, *p, dw, 1);
-  }
+  // the kernel visits every pixel the reference's loops visit: y, x in [boundary, size - boundary), val != 0 (:346-354)
+  launch_disparity(c, w, h, *p, dw, 1);
   if (disp) ODO_CUDA_OK(c, cudaMemcpyAsync(disp, dw.disp, npx * 4, cudaMemcpyDeviceToHost, c->stream));
   if (dep) ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
   if (match_x) ODO_CUDA_OK(c, cudaMemcpyAsync(match_x, dw.match_x, npx * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -570,6 +544,8 @@ int odo_compute_depth(odo_ctx* c, const float* left, const float* right, int w, 
   const size_t npx = (size_t)w * h;
   ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left, npx * 4, cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right, npx * 4, cudaMemcpyHostToDevice, c->stream));
+  dw.match_x = nullptr;  // test-hook planes, not outputs of this call (min_ssd == nullptr also makes the
+  dw.min_ssd = nullptr;  // exact integer path of the line search eligible, depth.cu k_quantize)
   launch_select(c, dl, dr, 0, w, h, *p, dw, 1);
   launch_disparity(c, w, h, *p, dw, 1);
   launch_depth_refine(c, dl, dr, 0, w, h, *p, dw, 1);

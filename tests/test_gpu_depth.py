@@ -52,6 +52,63 @@ def test_disparity_indices_bit_exact(ctx, pairs, i):
     assert bits_equal(ssd[sel], ossd[sel])          # the 8-tap SSD in the AVX tree order
 
 
+@pytest.mark.parametrize("i", range(3))
+def test_disparity_integer_path_bit_exact(ctx, pairs, i):
+    """Without the cost plane the library may take its exact integer path (u8-sourced frames blur to
+    multiples of 1/16): argmin columns, disparities and inverse depths must not change by a bit."""
+    L, R = pairs[i]
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    _, obl, obr, oval = oracle.select_pixels(L, R, op)
+    assert np.array_equal(obl * 16, np.rint(obl * 16))          # the premise of the integer path
+    orc, odisp, odep, omatch, ossd = oracle.disparity_search(obl, obr, oval, op)
+    rc, disp, dep, match, _ = ctx.disparity_search(obl, obr, oval, dp, want_ssd=False)
+    assert rc == 0 and orc == 0
+    assert np.array_equal(match, omatch)
+    assert bits_equal(disp, odisp) and bits_equal(dep, odep)
+
+
+def test_disparity_integer_path_extremes(ctx):
+    """Saturated contrast: 256*SSD reaches 8*4080^2 (no int32 overflow), costs above 2^16 are where
+    the fp32 reference rounds -- all of them rejected by ssd_th on both sides; ties between equal
+    integer costs resolve to the first column."""
+    h, w = 376, 1241
+    rng = np.random.default_rng(5)
+    R = (rng.integers(0, 2, (h, w)) * 255).astype(np.float32)
+    L = np.roll(R, 7, axis=1).copy()
+    L[:, ::3] = 255 - L[:, ::3]
+    op, dp = oracle.depth_params(), capi.default_depth_params()
+    bl, br = oracle.gaussian_blur3(L), oracle.gaussian_blur3(R)
+    val = np.zeros((h, w), np.uint8)
+    val[8:368:5, 12:1230:9] = 1
+    for th in (900.0, 20000.0, 65535.0):
+        op.ssd_th = dp.ssd_th = th
+        orc, odisp, odep, omatch, _ = oracle.disparity_search(bl, br, val, op)
+        rc, disp, dep, match, _ = ctx.disparity_search(bl, br, val, dp, want_ssd=False)
+        assert np.array_equal(match, omatch), th
+        assert bits_equal(disp, odisp) and bits_equal(dep, odep)
+
+
+def test_disparity_falls_back_to_fp32_for_inexact_input(ctx, pairs):
+    """Arbitrary float images (not multiples of 1/16): the integer path must switch itself off."""
+    L, R = pairs[0]
+    rng = np.random.default_rng(9)
+    Lf = (L + rng.random(L.shape).astype(np.float32) * 0.37).astype(np.float32)
+    Rf = (R + rng.random(R.shape).astype(np.float32) * 0.37).astype(np.float32)
+    dp, op = capi.default_depth_params(), oracle.depth_params()
+    _, obl, obr, oval = oracle.select_pixels(Lf, Rf, op)
+    orc, odisp, odep, omatch, _ = oracle.disparity_search(obl, obr, oval, op)
+    rc, disp, dep, match, _ = ctx.disparity_search(obl, obr, oval, dp, want_ssd=False)
+    assert np.array_equal(match, omatch) and bits_equal(disp, odisp) and bits_equal(dep, odep)
+    # one single inexact pixel is enough
+    bl1 = oracle.gaussian_blur3(L)
+    br1 = oracle.gaussian_blur3(R)
+    br1[200, 600] += np.float32(1.0 / 64)
+    _, _, _, oval1 = oracle.select_pixels(L, R, op)
+    orc, odisp, odep, omatch, _ = oracle.disparity_search(bl1, br1, oval1, op)
+    rc, disp, dep, match, _ = ctx.disparity_search(bl1, br1, oval1, dp, want_ssd=False)
+    assert np.array_equal(match, omatch) and bits_equal(disp, odisp) and bits_equal(dep, odep)
+
+
 def test_disparity_tie_break_first_minimum(ctx):
     """Periodic right image => many exactly equal SSD minima; the smallest column must win."""
     h, w = 376, 1241
@@ -66,6 +123,11 @@ def test_disparity_tie_break_first_minimum(ctx):
     rc, disp, dep, match, ssd = ctx.disparity_search(L, R, val, dp)
     assert np.array_equal(match, omatch) and bits_equal(disp, odisp)
     assert (omatch[val == 1] < 40).mean() > 0.9     # the period makes early columns win
+    # same through the integer path (ssd_th must stay below 2^16 for it to be eligible)
+    dp, op = capi.default_depth_params(ssd_th=60000.0), oracle.depth_params(ssd_th=60000.0)
+    orc, odisp, odep, omatch, ossd = oracle.disparity_search(L, R, val, op)
+    rc, disp, dep, match, _ = ctx.disparity_search(L, R, val, dp, want_ssd=False)
+    assert np.array_equal(match, omatch) and bits_equal(disp, odisp)
 
 
 @pytest.mark.parametrize("i", range(2))

@@ -5,7 +5,7 @@ import numpy as np, torch
 from odometry_b200 import capi
 import bench
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-fr = bench.render_sequences(S, 6, 0, "cuda").to(torch.float32)
+fr = bench.render_sequences(list(range(S)), 6, "cuda").to(torch.float32)
 ctx = capi.Context(0)
 trk = capi.Tracker(ctx, 1241, 376, 4, S)
 L = fr[:, :, 0].contiguous(); R = fr[:, :, 1].contiguous()
