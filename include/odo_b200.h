@@ -149,6 +149,16 @@ int  odo_tracker_step(odo_tracker* t, const float* const* left, const float* con
                       float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 int  odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right,
                          float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
+/* Pipelined ingest of the same loop: odo_tracker_enqueue[_u8] starts the host->device copy of one frame
+ * per sequence on a copy stream, queues the frame's kernels behind it and returns without waiting, so the
+ * copy of frame k+1 overlaps the kernels of frame k (the reference reads frame k+1 from disk while nothing
+ * else runs, run_odometry_kitti_offline.cpp:200).  At most two frames may be in flight.
+ * odo_tracker_collect blocks until the oldest frame in flight is done and returns its results.  The host
+ * buffers of a frame must stay valid (and should be pinned) until that frame has been collected.
+ * odo_tracker_step == enqueue + collect. */
+int  odo_tracker_enqueue(odo_tracker* t, const float* const* left, const float* const* right);
+int  odo_tracker_enqueue_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right);
+int  odo_tracker_collect(odo_tracker* t, float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 /* device-resident variant for the HBM-resident bench leg: images already on the device as one
  * contiguous [n_seq][h][w] float32 block per eye. */
 int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev,

@@ -52,6 +52,7 @@ EXPORTS = [
     "odo_compute_depth", "odo_select_pixels", "odo_disparity_search", "odo_depth_optimize",
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
     "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev", "odo_tracker_stage_ms",
+    "odo_tracker_enqueue", "odo_tracker_enqueue_u8", "odo_tracker_collect",
 ]
 STAGES = ["image_pyramid", "lm_solve", "blur_select", "disparity", "depth_refine", "depth_pyr_promote_prepare"]
 
@@ -290,6 +291,19 @@ class Tracker:
         la, ra = arr_t(*left_ptrs), arr_t(*right_ptrs)
         fn = lib().odo_tracker_step_u8 if u8 else lib().odo_tracker_step
         rc = fn(self.h, la, ra, *self._outs())
+        return self._result(rc)
+
+    def enqueue_ptrs(self, left_ptrs, right_ptrs, u8=False):
+        """Pipelined ingest: start the copies + kernels of one frame and return at once (<= 2 in flight)."""
+        arr_t = C.c_void_p * self.n
+        la, ra = arr_t(*left_ptrs), arr_t(*right_ptrs)
+        fn = lib().odo_tracker_enqueue_u8 if u8 else lib().odo_tracker_enqueue
+        if fn(self.h, la, ra) != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def collect(self):
+        """Results of the oldest frame in flight."""
+        rc = lib().odo_tracker_collect(self.h, *self._outs())
         return self._result(rc)
 
     def step(self, lefts, rights):

@@ -194,8 +194,14 @@ struct odo_tracker {
   int64_t npx = 0;
   int64_t pyr_stride = 0;   // floats per sequence pyramid (padded to 4)
   void* mem = nullptr;      // one device allocation
-  float *in_left = nullptr, *in_right = nullptr;
-  uint8_t* in_u8 = nullptr;
+  // two ingest slots: the host->device copy of frame k+1 (copy stream) overlaps the kernels of frame k
+  float *in_left[2] = {nullptr, nullptr}, *in_right[2] = {nullptr, nullptr};
+  uint8_t* in_u8[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // copy stream: the slot's frame is on the device
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // compute stream: the last kernel reading the slot's frame is queued
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};     // compute stream: the slot's results are in h_state[slot]
+  int64_t n_enqueued = 0, n_collected = 0;
   float *cur_img = nullptr, *kf_img = nullptr, *cur_dep = nullptr, *kf_dep = nullptr;
   DepthWork dw;
   LmLists lists;
@@ -204,28 +210,29 @@ struct odo_tracker {
   LmResult* res = nullptr;
   SeqState* state = nullptr;
   int* promote = nullptr;
-  SeqState* h_state = nullptr;  // pinned
+  SeqState* h_state[2] = {nullptr, nullptr};  // pinned, one per ingest slot
   int G_lm = 1;
   int frame_id = 0;
   // stage boundaries of the last step (bench.py roofline): 0 start, 1 image pyramid, 2 LM solve + pose,
   // 3 blur + selection, 4 disparity search, 5 depth refinement, 6 depth pyramid + promotion + LM prepare
-  cudaEvent_t ev[ODO_N_STAGES + 1] = {nullptr};
+  cudaEvent_t ev[2][ODO_N_STAGES + 1] = {{nullptr}};
   float stage_ms[ODO_N_STAGES] = {0};
 };
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* pose_abs, float* pose_kf,
-                         int* is_keyframe, int* status) {
+// queues all kernels of one frame (one frame per sequence) on the compute stream; no host wait
+static int tracker_launch(odo_tracker* t, const float* L, const float* R, int slot) {
   odo_ctx* c = t->c;
   const int n = t->n;
   const int first = (t->frame_id == 0) ? 1 : 0;
   const int64_t in_stride = t->npx;
+  cudaEvent_t* ev = t->ev[slot];
   c->err.clear();
-  cudaEventRecord(t->ev[0], c->stream);
+  cudaEventRecord(ev[0], c->stream);
   // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
   launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n);
-  cudaEventRecord(t->ev[1], c->stream);
+  cudaEventRecord(ev[1], c->stream);
   if (!first) {
     // Solve against the keyframe (:215)
     if (launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1) != 0)
@@ -233,14 +240,15 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
     k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
     c->launches++;
   }
-  cudaEventRecord(t->ev[2], c->stream);
+  cudaEventRecord(ev[2], c->stream);
   // ComputeDepth on every frame (:226-229), then DepthPyramid (:252)
   launch_select(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n, /*blur_left_done=*/true);
-  cudaEventRecord(t->ev[3], c->stream);
+  cudaEventRecord(ev[3], c->stream);
   launch_disparity(c, t->w, t->h, t->dp, t->dw, n);
-  cudaEventRecord(t->ev[4], c->stream);
+  cudaEventRecord(ev[4], c->stream);
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
-  cudaEventRecord(t->ev[5], c->stream);
+  cudaEventRecord(ev[5], c->stream);
+  cudaEventRecord(t->ev_consumed[slot], c->stream);  // nothing after this point reads the input frame
   launch_depth_pyramid(c, t->dw.dep, t->dw.dep_stride, t->cur_dep, t->pyr_stride, t->g, 0, n);
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
   // keyframe promotion (:258-265): the new keyframe's pyramids and LM point lists
@@ -253,22 +261,63 @@ static int tracker_frame(odo_tracker* t, const float* L, const float* R, float* 
   }
   launch_lm_prepare(c, t->kf_img, t->pyr_stride, t->kf_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote);
   t->lm.lambda = 0.01f;  // Reset(pose, 0.01f)
-  cudaEventRecord(t->ev[6], c->stream);
-  ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state, t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
-  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventRecord(ev[6], c->stream);
+  ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state[slot], t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
+  ODO_CUDA_OK(c, cudaEventRecord(t->ev_done[slot], c->stream));
   if (!c->err.empty()) return -1;
-  for (int i = 0; i < ODO_N_STAGES; i++) cudaEventElapsedTime(&t->stage_ms[i], t->ev[i], t->ev[i + 1]);
+  t->frame_id++;
+  return 0;
+}
+
+// waits for the frame queued in `slot` and unpacks its results
+static int tracker_finish(odo_tracker* t, int slot, float* pose_abs, float* pose_kf, int* is_keyframe, int* status) {
+  odo_ctx* c = t->c;
+  const int n = t->n;
+  ODO_CUDA_OK(c, cudaEventSynchronize(t->ev_done[slot]));
+  for (int i = 0; i < ODO_N_STAGES; i++) cudaEventElapsedTime(&t->stage_ms[i], t->ev[slot][i], t->ev[slot][i + 1]);
   int rc = 0;
   for (int b = 0; b < n; b++) {
-    const SeqState& s = t->h_state[b];
+    const SeqState& s = t->h_state[slot][b];
     if (pose_abs) std::memcpy(pose_abs + 16 * b, s.cur_pose, sizeof(float) * 16);
     if (pose_kf) std::memcpy(pose_kf + 16 * b, s.pose_kf, sizeof(float) * 16);
     if (is_keyframe) is_keyframe[b] = s.promote;
     if (status) status[b] = s.status;
     if (s.status != 0) rc = -1;
   }
-  t->frame_id++;
   return rc;
+}
+
+// starts the host->device copies of one frame on the copy stream and queues the frame behind them
+template <typename T>
+static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const* right) {
+  if (!t || !left || !right) return -1;
+  odo_ctx* c = t->c;
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  if (t->n_enqueued - t->n_collected >= 2) {
+    c->err = "tracker: two frames are already in flight, collect one first";
+    return -1;
+  }
+  const int slot = (int)(t->n_enqueued & 1);
+  const bool u8 = sizeof(T) == 1;
+  // the slot's previous frame (two enqueues ago) must have been consumed by its kernels
+  if (t->n_enqueued >= 2) ODO_CUDA_OK(c, cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[slot], 0));
+  const size_t bytes = sizeof(T) * (size_t)t->npx;
+  for (int b = 0; b < t->n; b++) {
+    void* dl = u8 ? (void*)(t->in_u8[slot] + (size_t)b * t->npx) : (void*)(t->in_left[slot] + (size_t)b * t->npx);
+    void* dr = u8 ? (void*)(t->in_u8[slot] + (size_t)(t->n + b) * t->npx) : (void*)(t->in_right[slot] + (size_t)b * t->npx);
+    ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
+    ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
+  }
+  ODO_CUDA_OK(c, cudaEventRecord(t->ev_copied[slot], t->copy_stream));
+  ODO_CUDA_OK(c, cudaStreamWaitEvent(c->stream, t->ev_copied[slot], 0));
+  if (u8) {
+    // gray_8u.convertTo(gray, CV_32F), run_odometry_kitti_offline.cpp:348,358
+    launch_u8_to_f32(c, t->in_u8[slot], t->in_left[slot], t->npx * t->n);
+    launch_u8_to_f32(c, t->in_u8[slot] + (size_t)t->n * t->npx, t->in_right[slot], t->npx * t->n);
+  }
+  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot) != 0) return -1;
+  t->n_enqueued++;
+  return 0;
 }
 
 extern "C" {
@@ -311,7 +360,7 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   const size_t rs_b = al256(sizeof(LmResult) * n_seq);
   const size_t st_b = al256(sizeof(SeqState) * n_seq);
   const size_t pf_b = al256(sizeof(int) * n_seq);
-  bytes = in_b * 2 + u8_b + pyr_b * 4 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
+  bytes = (in_b * 2 + u8_b) * 2 + pyr_b * 4 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
   if (cudaMalloc(&t->mem, bytes) != cudaSuccess) {
     c->err = "tracker: cudaMalloc failed";
     delete t;
@@ -319,9 +368,11 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   }
   cudaMemsetAsync(t->mem, 0, bytes, c->stream);
   char* p = (char*)t->mem;
-  t->in_left = (float*)p; p += in_b;
-  t->in_right = (float*)p; p += in_b;
-  t->in_u8 = (uint8_t*)p; p += u8_b;
+  for (int k = 0; k < 2; k++) {
+    t->in_left[k] = (float*)p; p += in_b;
+    t->in_right[k] = (float*)p; p += in_b;
+    t->in_u8[k] = (uint8_t*)p; p += u8_b;
+  }
   t->cur_img = (float*)p; p += pyr_b;
   t->kf_img = (float*)p; p += pyr_b;
   t->cur_dep = (float*)p; p += pyr_b;
@@ -341,13 +392,20 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   t->res = (LmResult*)p; p += rs_b;
   t->state = (SeqState*)p; p += st_b;
   t->promote = (int*)p; p += pf_b;
-  if (cudaMallocHost(&t->h_state, sizeof(SeqState) * n_seq) != cudaSuccess) {
+  if (cudaMallocHost(&t->h_state[0], sizeof(SeqState) * n_seq * 2) != cudaSuccess) {
     cudaFree(t->mem);
     delete t;
     c->err = "tracker: cudaMallocHost failed";
     return -1;
   }
-  for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[i]);
+  t->h_state[1] = t->h_state[0] + n_seq;
+  cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 2; k++) {
+    for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[k][i]);
+    cudaEventCreateWithFlags(&t->ev_copied[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_consumed[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming);
+  }
   k_track_init<<<(n_seq + 63) / 64, 64, 0, c->stream>>>(t->state, t->T_init, n_seq);
   c->launches++;
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -359,10 +417,19 @@ void odo_tracker_destroy(odo_tracker* t) {
   if (!t) return;
   cudaSetDevice(t->c->device);
   cudaStreamSynchronize(t->c->stream);
+  if (t->copy_stream) {
+    cudaStreamSynchronize(t->copy_stream);
+    cudaStreamDestroy(t->copy_stream);
+  }
   cudaFree(t->mem);
-  cudaFreeHost(t->h_state);
-  for (int i = 0; i <= ODO_N_STAGES; i++)
-    if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+  cudaFreeHost(t->h_state[0]);
+  for (int k = 0; k < 2; k++) {
+    for (int i = 0; i <= ODO_N_STAGES; i++)
+      if (t->ev[k][i]) cudaEventDestroy(t->ev[k][i]);
+    if (t->ev_copied[k]) cudaEventDestroy(t->ev_copied[k]);
+    if (t->ev_consumed[k]) cudaEventDestroy(t->ev_consumed[k]);
+    if (t->ev_done[k]) cudaEventDestroy(t->ev_done[k]);
+  }
   delete t;
 }
 
@@ -383,41 +450,47 @@ int odo_tracker_stage_ms(const odo_tracker* t, float* ms_out) {
   return 0;
 }
 
+int odo_tracker_enqueue(odo_tracker* t, const float* const* left, const float* const* right) {
+  return tracker_enqueue<float>(t, left, right);
+}
+
+int odo_tracker_enqueue_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right) {
+  return tracker_enqueue<uint8_t>(t, left, right);
+}
+
+int odo_tracker_collect(odo_tracker* t, float* pose_abs, float* pose_kf, int* is_keyframe, int* status) {
+  if (!t) return -1;
+  if (t->n_collected >= t->n_enqueued) {
+    t->c->err = "tracker: nothing in flight";
+    return -1;
+  }
+  const int slot = (int)(t->n_collected & 1);
+  t->n_collected++;
+  return tracker_finish(t, slot, pose_abs, pose_kf, is_keyframe, status);
+}
+
 int odo_tracker_step(odo_tracker* t, const float* const* left, const float* const* right, float* pose_abs,
                      float* pose_kf, int* is_keyframe, int* status) {
-  if (!t || !left || !right) return -1;
-  odo_ctx* c = t->c;
-  ODO_CUDA_OK(c, cudaSetDevice(c->device));
-  const size_t bytes = sizeof(float) * t->npx;
-  for (int b = 0; b < t->n; b++) {
-    ODO_CUDA_OK(c, cudaMemcpyAsync(t->in_left + b * t->npx, left[b], bytes, cudaMemcpyHostToDevice, c->stream));
-    ODO_CUDA_OK(c, cudaMemcpyAsync(t->in_right + b * t->npx, right[b], bytes, cudaMemcpyHostToDevice, c->stream));
-  }
-  return tracker_frame(t, t->in_left, t->in_right, pose_abs, pose_kf, is_keyframe, status);
+  if (!t || t->n_enqueued != t->n_collected) return -1;
+  if (tracker_enqueue<float>(t, left, right) != 0) return -1;
+  return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
 int odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right, float* pose_abs,
                         float* pose_kf, int* is_keyframe, int* status) {
-  if (!t || !left || !right) return -1;
-  odo_ctx* c = t->c;
-  ODO_CUDA_OK(c, cudaSetDevice(c->device));
-  uint8_t* l8 = t->in_u8;
-  uint8_t* r8 = t->in_u8 + t->npx * t->n;
-  for (int b = 0; b < t->n; b++) {
-    ODO_CUDA_OK(c, cudaMemcpyAsync(l8 + b * t->npx, left[b], (size_t)t->npx, cudaMemcpyHostToDevice, c->stream));
-    ODO_CUDA_OK(c, cudaMemcpyAsync(r8 + b * t->npx, right[b], (size_t)t->npx, cudaMemcpyHostToDevice, c->stream));
-  }
-  // gray_8u.convertTo(gray, CV_32F), run_odometry_kitti_offline.cpp:348,358
-  launch_u8_to_f32(c, l8, t->in_left, t->npx * t->n);
-  launch_u8_to_f32(c, r8, t->in_right, t->npx * t->n);
-  return tracker_frame(t, t->in_left, t->in_right, pose_abs, pose_kf, is_keyframe, status);
+  if (!t || t->n_enqueued != t->n_collected) return -1;
+  if (tracker_enqueue<uint8_t>(t, left, right) != 0) return -1;
+  return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
 int odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev, float* pose_abs,
                          float* pose_kf, int* is_keyframe, int* status) {
-  if (!t || !left_dev || !right_dev) return -1;
+  if (!t || !left_dev || !right_dev || t->n_enqueued != t->n_collected) return -1;
   ODO_CUDA_OK(t->c, cudaSetDevice(t->c->device));
-  return tracker_frame(t, left_dev, right_dev, pose_abs, pose_kf, is_keyframe, status);
+  const int slot = (int)(t->n_enqueued & 1);
+  if (tracker_launch(t, left_dev, right_dev, slot) != 0) return -1;
+  t->n_enqueued++;
+  return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
 // ---- single-call depth entry points (batch = 1 over the same kernels) ------------------------------------

@@ -91,3 +91,34 @@ def test_depth_failure_ends_the_sequence(ctx):
     rc, pa, pk, kf, st = t.step([flat], [flat])
     assert rc == -1 and st[0] == -1
     t.close()
+
+
+def test_pipelined_ingest_equals_synchronous_steps(ctx, synth_data):
+    """odo_tracker_enqueue / odo_tracker_collect (copy of frame k+1 overlapping the kernels of frame k)
+    returns, frame by frame, exactly what odo_tracker_step returns; a third enqueue is refused."""
+    import torch
+    seqs = [synth_data.sequence(s, n_frames=5) for s in (0, 1)]
+    sync = capi.Tracker(ctx, 1241, 376, 4, 2)
+    want = [sync.step([s["frames"][k][0] for s in seqs], [s["frames"][k][1] for s in seqs]) for k in range(5)]
+    sync.close()
+    for u8 in (True, False):
+        dt = torch.uint8 if u8 else torch.float32
+        host = [[(torch.from_numpy(L.copy()).to(dt).pin_memory(), torch.from_numpy(R.copy()).to(dt).pin_memory())
+                 for L, R in s["frames"]] for s in seqs]
+        t = capi.Tracker(ctx, 1241, 376, 4, 2)
+
+        def enq(k):
+            t.enqueue_ptrs([h[k][0].data_ptr() for h in host], [h[k][1].data_ptr() for h in host], u8=u8)
+
+        enq(0)
+        for k in range(5):
+            if k + 1 < 5:
+                enq(k + 1)
+                if k == 0:
+                    with pytest.raises(capi.OdoError):
+                        enq(2)           # two frames already in flight
+            rc, pa, pk, kf, st = t.collect()
+            assert rc == 0
+            assert np.array_equal(pa, want[k][1]) and np.array_equal(pk, want[k][2])
+            assert np.array_equal(kf, want[k][3])
+        t.close()
