@@ -148,7 +148,7 @@ struct DepthWork {
   int* sel_xy;         // [batch][cap] packed (y << 16 | x), -1 = hole; block-major selection order
   int* sel_count;      // [batch][512] per 16x32 block
   odo_depth_stats* stats;  // [batch]
-  float* ref_state;    // refinement scratch [batch][6][cap]
+  float* ref_state;    // refinement scratch, 24 bytes per slot (depth.cu, k_refine)
   int cap;             // pixel-list capacity per sequence
   int64_t blurL_stride;  // elements between sequences in blurL (the tracker aliases level 0 of the image pyramid)
   int64_t dep_stride;    // elements between sequences in dep (the tracker aliases level 0 of the depth pyramid)
@@ -158,6 +158,14 @@ struct DepthWork {
   uint16_t* qR;
   int* eR;             // [batch][w*h]
   int* exact;          // [batch]
+  // raw (unblurred) right image as u8 for the refinement (depth.cu, k_refine): rawR8 == nullptr makes
+  // launch_depth_refine build it into rawR8_own from the float frame; a caller that already has the u8
+  // frame on the device points rawR8 at it and sets raw_exact[b] = 1 itself
+  const uint8_t* rawR8;
+  int64_t rawR8_stride;
+  uint8_t* rawR8_own;
+  int* raw_exact;      // [batch]
+  long long* dbg;      // [16] cycle counters of sequence 0 / CTA 0 of the refinement (profiling aid)
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)

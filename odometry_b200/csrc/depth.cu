@@ -436,9 +436,16 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
 // ---- inverse-depth refinement ---------------------------------------------------------------------------
 // One pass over the pixel list per LM iteration: the update decided by the previous iteration's GLOBAL
 // accept/reject (:147-165) is applied to a slot and the new tmp_depth is evaluated (:200-242) in the same
-// visit, so a slot costs one dependent chain of global accesses per iteration; kRefUnroll independent
+// visit, so a slot costs one dependent chain of memory accesses per iteration; kRefUnroll independent
 // slots per thread keep that many chains in flight.
-constexpr int kRefThreads = 512;
+// Memory behaviour decides this kernel (64 sequences x 40 960 slots x ~11 iterations): per slot and
+// iteration it needs the slot state (5 floats, coalesced, 52 MB for the batch: L2 resident) and three
+// neighbouring texels of the RAW right image at a data-dependent column.  As float planes the right
+// images of a batch (120 MB) do not fit in L2 next to the state and every visit costs a 32-byte DRAM
+// sector; u8-sourced frames (the reference's only input) are therefore also kept as a u8 plane (30 MB,
+// four times as many texels per sector), which k_raw8 builds -- or the u8 ingest path already has --
+// together with a per-sequence "every texel is an integer in [0, 255]" flag; other sequences read floats.
+constexpr int kRefThreads = 256;
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kRefUnroll = 4;
 
@@ -449,7 +456,148 @@ struct RefShared {
 
 enum { PEND_NONE = 0, PEND_ACCEPT = 1, PEND_REJECT = 2 };
 
-__global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
+__global__ void __launch_bounds__(256) k_raw8(const float* __restrict__ R, int64_t stride, int64_t npx, uint8_t* __restrict__ out,
+                                              int* __restrict__ exact) {
+  const int b = blockIdx.y;
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  bool bad = false;
+  if (i < npx) {
+    const float* src = R + b * stride + i;
+    uint8_t* dst = out + b * npx + i;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i + k < npx) {
+        const float v = __ldg(src + k);
+        const bool ok = v >= 0.0f && v <= 255.0f && v == rintf(v);
+        bad |= !ok;
+        dst[k] = ok ? (uint8_t)(int)v : 0;
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&exact[b], 0);
+}
+
+struct RefTexels {  // R[wx-1], R[wx], R[wx+1] as floats
+  float m, c, p;
+};
+
+__device__ __forceinline__ RefTexels ref_texels(const float* __restrict__ Rf, const uint8_t* __restrict__ R8, bool use8,
+                                                int64_t o) {
+  RefTexels t;
+  if (use8) {
+    t.m = (float)__ldg(R8 + o - 1);
+    t.c = (float)__ldg(R8 + o);
+    t.p = (float)__ldg(R8 + o + 1);
+  } else {
+    t.m = __ldg(Rf + o - 1);
+    t.c = __ldg(Rf + o);
+    t.p = __ldg(Rf + o + 1);
+  }
+  return t;
+}
+
+// One pass over the slot list: apply the decision of the previous iteration, take the LM step and
+// evaluate the new tmp_depth.  FIRST: the pass that also builds the slot records from the pixel list.
+// The kernel is bound by instruction issue (about 100 instructions per slot visit), so everything that is
+// uniform over the pass (the pending decision, 1 + lambda) is folded into selects on uniform values.
+struct RefPass {
+  const float* __restrict__ L;
+  const float* __restrict__ R;
+  const uint8_t* __restrict__ R8;
+  float* dep;
+  const int* __restrict__ sel_xy;
+  float4* __restrict__ st_a;   // {current, tmp, jtwj, b}
+  int2* __restrict__ st_b;     // {y << 16 | x, left intensity}
+  int W, nslots, tid, nthreads;
+  float txfx, gscale, wmax, huber_delta;
+  bool use8;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool accepted_once, float lambda,
+                                            double& err_sum, int& err_cnt) {
+  // current <- tmp on accept ; current <- pre (zero until something was accepted) on the first rejects
+  const bool take_tmp = pending == PEND_ACCEPT;
+  const bool zero_cur = pending == PEND_REJECT && !accepted_once;
+  const bool step = pending != PEND_NONE;
+  for (int s0 = rp.tid; s0 < rp.nslots; s0 += rp.nthreads * kRefUnroll) {
+    float4 sa[kRefUnroll];
+    int2 sb[kRefUnroll];
+#pragma unroll
+    for (int u = 0; u < kRefUnroll; u++) {
+      const int s = s0 + u * rp.nthreads;
+      sa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sb[u] = make_int2(-1, 0);
+      if (s < rp.nslots) {
+        if (FIRST) {
+          sb[u].x = rp.sel_xy[s];
+        } else {
+          sb[u] = rp.st_b[s];
+          sa[u] = rp.st_a[s];
+        }
+      }
+    }
+    if (FIRST) {
+#pragma unroll
+      for (int u = 0; u < kRefUnroll; u++) {
+        if (sb[u].x < 0) continue;
+        const int o = (sb[u].x >> 16) * rp.W + (sb[u].x & 0xffff);
+        sb[u].y = __float_as_int(__ldg(rp.L + o));
+        const float d0 = rp.dep[o];  // init_depth / current_depth / tmp_depth, :105-139
+        sa[u].x = d0;
+        sa[u].y = d0;
+      }
+    }
+    float wf[kRefUnroll];
+    RefTexels tx[kRefUnroll];
+#pragma unroll
+    for (int u = 0; u < kRefUnroll; u++) {
+      float cur = take_tmp ? sa[u].y : sa[u].x;
+      cur = zero_cur ? 0.f : cur;
+      float tmp = sa[u].y;
+      if (!FIRST && step) {
+        // A = jtwj + lambda*jtwj ; delta = A.inverse() * b ; tmp = delta + current, :162-165
+        // (1/A correctly rounded: __frcp_rn is the IEEE reciprocal, identical to 1.0f / A)
+        const float A = __fadd_rn(sa[u].z, __fmul_rn(lambda, sa[u].z));
+        tmp = __fadd_rn(__fmul_rn(__frcp_rn(A), sa[u].w), cur);
+      }
+      sa[u].x = cur;
+      sa[u].y = tmp;
+      // ComputeResidualJacobian(tmp_depth), :200-242
+      const int x = sb[u].x & 0xffff;
+      wf[u] = floorf(__fsub_rn((float)x, __fmul_rn(rp.txfx, tmp)));
+      // holes (yx < 0) and out-of-range columns (also NaN: int(NaN) is INT_MIN on x86, i.e. "< 2") load nothing
+      const bool in = sb[u].x >= 0 && wf[u] >= 2.0f && wf[u] <= rp.wmax;
+      wf[u] = in ? wf[u] : -1.0f;
+      tx[u].m = tx[u].c = tx[u].p = 0.f;
+      if (in) tx[u] = ref_texels(rp.R, rp.R8, rp.use8, (sb[u].x >> 16) * rp.W + (int)wf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kRefUnroll; u++) {
+      const int s = s0 + u * rp.nthreads;
+      if (sb[u].x < 0) {
+        if (FIRST && s < rp.nslots) rp.st_b[s] = sb[u];  // holes stay holes for the later passes
+        continue;
+      }
+      float njt = 0.f, nbv = 0.f;
+      if (wf[u] >= 0.0f) {
+        const float r_i = __fsub_rn(__int_as_float(sb[u].y), tx[u].c);
+        const float ar = fabsf(r_i);
+        float w_i = 1.0f;
+        if (ar > rp.huber_delta) w_i = __fdiv_rn(rp.huber_delta, ar);
+        const float g = __fmul_rn(rp.gscale, __fsub_rn(tx[u].p, tx[u].m));
+        err_sum += (double)__fmul_rn(__fmul_rn(r_i, r_i), w_i);
+        err_cnt++;
+        njt = __fmul_rn(__fmul_rn(g, g), w_i);
+        nbv = __fmul_rn(__fmul_rn(-g, w_i), r_i);
+      }
+      rp.st_a[s] = make_float4(sa[u].x, sa[u].y, njt, nbv);
+      if (FIRST) rp.st_b[s] = sb[u];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
                                                           int64_t stride, int W, int H, odo_depth_params p,
                                                           DepthWork d, double* partials, unsigned* barrier,
                                                           int* abort_flag) {
@@ -464,21 +612,27 @@ __global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restri
   gs.parity = 0;
   gs.G = G;
   const int64_t npx = (int64_t)W * H;
-  const float* __restrict__ L = Limg + b * stride;
-  const float* __restrict__ R = Rimg + b * stride;
+  odo_depth_stats* stats = d.stats + b;
   float* dep = d.dep + b * d.dep_stride;
   uint8_t* val = d.val + b * npx;
+  RefPass rp;
+  rp.L = Limg + b * stride;
+  rp.R = Rimg + b * stride;
+  rp.use8 = d.rawR8 != nullptr && d.raw_exact[b] != 0;
+  rp.R8 = d.rawR8 ? d.rawR8 + b * d.rawR8_stride : nullptr;
+  rp.dep = dep;
   // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
-  const int nslots = d.cap;
-  const int* __restrict__ sel_xy = d.sel_xy + (int64_t)b * nslots;
-  float* st_cur = d.ref_state + (int64_t)b * 6 * nslots;
-  float* st_tmp = st_cur + nslots;
-  float* st_res = st_tmp + nslots;
-  float* st_jt = st_res + nslots;
-  float* st_bv = st_jt + nslots;
-  odo_depth_stats* stats = d.stats + b;
-  const int tid = blockIdx.x * kRefThreads + threadIdx.x;
-  const int nthreads = G * kRefThreads;
+  rp.nslots = d.cap;
+  rp.sel_xy = d.sel_xy + (int64_t)b * rp.nslots;
+  rp.st_a = reinterpret_cast<float4*>(d.ref_state) + (int64_t)b * rp.nslots;
+  rp.st_b = reinterpret_cast<int2*>(d.ref_state + (int64_t)gridDim.y * 4 * rp.nslots) + (int64_t)b * rp.nslots;
+  rp.W = W;
+  rp.tid = blockIdx.x * kRefThreads + threadIdx.x;
+  rp.nthreads = G * kRefThreads;
+  rp.txfx = __fmul_rn(p.baseline, p.fx);  // tx * fx
+  rp.gscale = __fmul_rn(rp.txfx, 0.5f);
+  rp.wmax = (float)(W - 2);
+  rp.huber_delta = p.huber_delta;
   const int n_sel = stats->n_selected;            // written by k_select (previous launch)
   const bool too_many = n_sel > p.max_residuals;  // quirk Q7: the reference would overflow init_depth
 
@@ -488,77 +642,23 @@ __global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restri
   int pending = PEND_NONE;      // decision of the previous iteration, not yet applied to the slots
   bool accepted_once = false;   // pre_depth is all zeros until the first accepted estimate
   bool first = true;
-  const float txfx = __fmul_rn(p.baseline, p.fx);  // tx * fx
-  const float gscale = __fmul_rn(txfx, 0.5f);
-  const float wmax = (float)(W - 2);
+  long long cyc_first = 0, cyc_pass = 0, cyc_red = 0;
+  const long long t_begin = clock64();
   while (!too_many && p.max_iters > iter_count) {
-    double acc[2] = {0.0, 0.0};
-    for (int s0 = tid; s0 < nslots; s0 += nthreads * kRefUnroll) {
-      int yx[kRefUnroll];
-      float cur[kRefUnroll], tmp[kRefUnroll], jt[kRefUnroll], bv[kRefUnroll], lv[kRefUnroll];
-#pragma unroll
-      for (int u = 0; u < kRefUnroll; u++) {
-        const int s = s0 + u * nthreads;
-        yx[u] = (s < nslots) ? sel_xy[s] : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < kRefUnroll; u++) {
-        const int s = s0 + u * nthreads;
-        cur[u] = tmp[u] = jt[u] = bv[u] = lv[u] = 0.f;
-        if (yx[u] >= 0) {
-          const int64_t o = (int64_t)(yx[u] >> 16) * W + (yx[u] & 0xffff);
-          lv[u] = __ldg(L + o);
-          if (first) {
-            cur[u] = tmp[u] = dep[o];  // init_depth / current_depth / tmp_depth, :105-139
-          } else {
-            cur[u] = st_cur[s];
-            tmp[u] = st_tmp[s];
-            jt[u] = st_jt[s];
-            bv[u] = st_bv[s];
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kRefUnroll; u++) {
-        if (yx[u] < 0) continue;
-        const int s = s0 + u * nthreads;
-        const int y = yx[u] >> 16, x = yx[u] & 0xffff;
-        if (pending == PEND_ACCEPT) cur[u] = tmp[u];                    // current = tmp ; pre = current
-        else if (pending == PEND_REJECT && !accepted_once) cur[u] = 0.f;  // current = pre (still zero)
-        if (pending != PEND_NONE) {
-          // A = jtwj + lambda*jtwj ; delta = A.inverse() * b ; tmp = delta + current, :162-165
-          const float A = __fadd_rn(jt[u], __fmul_rn(lambda, jt[u]));
-          tmp[u] = __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, A), bv[u]), cur[u]);
-        }
-        // ComputeResidualJacobian(tmp_depth), :200-242
-        const float wf = floorf(__fsub_rn((float)x, __fmul_rn(txfx, tmp[u])));
-        float res, njt = 0.f, nbv = 0.f;
-        if (!(wf >= 2.0f && wf <= wmax)) {  // also catches NaN (int(NaN) is INT_MIN on x86, i.e. "< 2")
-          res = -1000.f;
-        } else {
-          const float* rrow = R + (int64_t)y * W + (int)wf;
-          const float r_i = __fsub_rn(lv[u], __ldg(rrow));
-          const float ar = fabsf(r_i);
-          const float w_i = (ar <= p.huber_delta) ? 1.0f : __fdiv_rn(p.huber_delta, ar);
-          const float g = __fmul_rn(gscale, __fsub_rn(__ldg(rrow + 1), __ldg(rrow - 1)));
-          res = ar;
-          acc[0] += (double)__fmul_rn(__fmul_rn(r_i, r_i), w_i);
-          acc[1] += 1.0;
-          njt = __fmul_rn(__fmul_rn(g, g), w_i);
-          nbv = __fmul_rn(__fmul_rn(-g, w_i), r_i);
-        }
-        st_cur[s] = cur[u];
-        st_tmp[s] = tmp[u];
-        st_res[s] = res;
-        st_jt[s] = njt;
-        st_bv[s] = nbv;
-      }
-    }
+    const long long t0 = clock64();
+    double err_sum = 0.0;
+    int err_cnt = 0;
+    if (first) refine_pass<true>(rp, pending, accepted_once, lambda, err_sum, err_cnt);
+    else refine_pass<false>(rp, pending, accepted_once, lambda, err_sum, err_cnt);
+    const long long t1 = clock64();
+    if (first) cyc_first += t1 - t0; else cyc_pass += t1 - t0;
     first = false;
     if (pending == PEND_ACCEPT) accepted_once = true;
+    double acc[2] = {err_sum, (double)err_cnt};
     group_allreduce<2, kRefWarps>(acc, sh.warp, sh.tot, gs);
     err_now = (float)(sh.tot[0] / sh.tot[1]);
     __syncthreads();
+    cyc_red += clock64() - t1;
     if (*(volatile int*)abort_flag) { pending = PEND_NONE; break; }
     if (err_now > err_last) {  // :147-151
       lambda = lambda * 10.0f;
@@ -573,16 +673,31 @@ __global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restri
     }
     iter_count++;
   }
-  // apply the last decision to current_depth, then write-back and filters, :176-191
+  const long long t_loop_end = clock64();
+  // apply the last decision to current_depth, then write-back and filters, :176-191.  The residual the
+  // filter looks at is the one of the LAST evaluated tmp_depth: re-evaluated here from the same inputs.
   double nv[1] = {0.0};
-  for (int s = tid; s < nslots && !too_many; s += nthreads) {
-    const int yx = sel_xy[s];
+  for (int s = rp.tid; s < rp.nslots && !too_many; s += rp.nthreads) {
+    const int yx = first ? rp.sel_xy[s] : rp.st_b[s].x;
     if (yx < 0) continue;
-    const int64_t o = (int64_t)(yx >> 16) * W + (yx & 0xffff);
-    float cur = first ? dep[o] : st_cur[s];
-    const float res = first ? 0.f : st_res[s];
-    if (pending == PEND_ACCEPT) cur = st_tmp[s];
-    else if (pending == PEND_REJECT && !accepted_once) cur = 0.f;
+    const int y = yx >> 16, x = yx & 0xffff;
+    const int o = y * W + x;
+    float cur, res = 0.f;  // residuals are all zero when no iteration ran
+    if (first) {
+      cur = dep[o];
+    } else {
+      const float4 a = rp.st_a[s];
+      cur = a.x;
+      const float wf = floorf(__fsub_rn((float)x, __fmul_rn(rp.txfx, a.y)));
+      if (!(wf >= 2.0f && wf <= rp.wmax)) {
+        res = -1000.f;
+      } else {
+        const RefTexels t = ref_texels(rp.R, rp.R8, rp.use8, y * W + (int)wf);
+        res = fabsf(__fsub_rn(__int_as_float(rp.st_b[s].y), t.c));
+      }
+      if (pending == PEND_ACCEPT) cur = a.y;
+      else if (pending == PEND_REJECT && !accepted_once) cur = 0.f;
+    }
     bool ok;
     if (res > p.photo_th || res == -1000.f) ok = false;
     else {
@@ -602,6 +717,10 @@ __global__ void __launch_bounds__(kRefThreads, 2) k_refine(const float* __restri
     int status = (n_valid < 500) ? -1 : 0;  // :192-197
     if (too_many || *(volatile int*)abort_flag) status = -1;
     stats->status = status;
+    if (b == 0 && d.dbg) {
+      d.dbg[0] = cyc_first; d.dbg[1] = cyc_pass; d.dbg[2] = cyc_red; d.dbg[3] = t_loop_end - t_begin;
+      d.dbg[4] = clock64() - t_loop_end; d.dbg[5] = iter_count; d.dbg[6] = G; d.dbg[7] = n_sel;
+    }
   }
 }
 
@@ -619,7 +738,8 @@ size_t depth_work_bytes(int w, int h, int batch, bool debug) {
   bytes += al((size_t)batch * kGridBlocks * kSelMax * 4);       // sel_xy
   bytes += al((size_t)batch * kGridBlocks * 4);                 // sel_count
   bytes += al((size_t)batch * sizeof(odo_depth_stats));
-  bytes += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);   // refinement state
+  bytes += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);   // refinement state: 16 + 8 bytes per slot
+  bytes += al(npx) + al((size_t)batch * 4) + 256;               // raw right image as u8, raw_exact, dbg
   const size_t qpx = (size_t)q_pitch(w) * h * batch + 16;  // +16: the staging reads whole 16-byte vectors
   bytes += al(qpx * 2) * 2 + al(qpx * 4) + al((size_t)batch * 4);  // qL, qR, eR, exact
   return bytes;
@@ -650,7 +770,12 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->qL = (uint16_t*)p; p += al(qpx * 2);
   d->qR = (uint16_t*)p; p += al(qpx * 2);
   d->eR = (int*)p; p += al(qpx * 4);
-  d->exact = (int*)p;
+  d->exact = (int*)p; p += al((size_t)batch * 4);
+  d->rawR8_own = (uint8_t*)p; p += al(npx);
+  d->raw_exact = (int*)p; p += al((size_t)batch * 4);
+  d->dbg = (long long*)p;
+  d->rawR8 = nullptr;      // set per call: the u8 ingest path points it at the frame it already has
+  d->rawR8_stride = (int64_t)w * h;
   d->cap = kGridBlocks * kSelMax;
   d->blurL_stride = (int64_t)w * h;
   d->dep_stride = (int64_t)w * h;
@@ -736,6 +861,15 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
   unsigned* barrier = (unsigned*)q; q += al(sizeof(unsigned) * batch);
   int* abort_flag = (int*)q;
   cudaMemsetAsync(barrier, 0, al(sizeof(unsigned) * batch) + 256, c->stream);
+  if (d.rawR8 == nullptr && d.rawR8_own != nullptr) {
+    // float ingest: derive the u8 plane (and learn per sequence whether it is exact)
+    const int64_t npx = (int64_t)w * h;
+    cudaMemsetAsync(d.raw_exact, 0xff, sizeof(int) * batch, c->stream);
+    k_raw8<<<dim3((unsigned)((npx + 1023) / 1024), batch), 256, 0, c->stream>>>(R, stride, npx, d.rawR8_own, d.raw_exact);
+    c->launches++;
+    d.rawR8 = d.rawR8_own;
+    d.rawR8_stride = npx;
+  }
   dim3 grid(G, batch), block(kRefThreads);
   cudaError_t e;
   if (G > 1) {

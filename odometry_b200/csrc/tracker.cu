@@ -222,7 +222,8 @@ struct odo_tracker {
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 // queues all kernels of one frame (one frame per sequence) on the compute stream; no host wait
-static int tracker_launch(odo_tracker* t, const float* L, const float* R, int slot) {
+// R8: the raw right frames as u8 when the caller already has them on the device (u8 ingest), else nullptr
+static int tracker_launch(odo_tracker* t, const float* L, const float* R, int slot, const uint8_t* R8 = nullptr) {
   odo_ctx* c = t->c;
   const int n = t->n;
   const int first = (t->frame_id == 0) ? 1 : 0;
@@ -246,6 +247,9 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   cudaEventRecord(ev[3], c->stream);
   launch_disparity(c, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(ev[4], c->stream);
+  t->dw.rawR8 = R8;
+  t->dw.rawR8_stride = t->npx;
+  if (R8) cudaMemsetAsync(t->dw.raw_exact, 0xff, sizeof(int) * n, c->stream);  // u8 frames are exact by construction
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(ev[5], c->stream);
   cudaEventRecord(t->ev_consumed[slot], c->stream);  // nothing after this point reads the input frame
@@ -315,7 +319,8 @@ static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const*
     launch_u8_to_f32(c, t->in_u8[slot], t->in_left[slot], t->npx * t->n);
     launch_u8_to_f32(c, t->in_u8[slot] + (size_t)t->n * t->npx, t->in_right[slot], t->npx * t->n);
   }
-  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot) != 0) return -1;
+  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, u8 ? t->in_u8[slot] + (size_t)t->n * t->npx : nullptr) != 0)
+    return -1;
   t->n_enqueued++;
   return 0;
 }
@@ -442,6 +447,12 @@ extern "C" int odo_tracker_lm_cycles(odo_tracker* t, long long out[8], int iters
   out[4] = r.cyc_dbg[0]; out[5] = r.cyc_dbg[1]; out[6] = r.cyc_dbg[2];
   for (int i = 0; i < 8; i++) iters[i] = r.iters[i];
   return 0;
+}
+
+// profiling aid (not in the public header): cycle split of k_refine for sequence 0 of the last step
+extern "C" int odo_tracker_refine_cycles(odo_tracker* t, long long out[8]) {
+  if (!t || !t->dw.dbg) return -1;
+  return cudaMemcpy(out, t->dw.dbg, sizeof(long long) * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 
 int odo_tracker_stage_ms(const odo_tracker* t, float* ms_out) {
