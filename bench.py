@@ -309,7 +309,11 @@ def main():
         trk.close()
         del host, host8
 
-    # ---------------- roofline of the dominant stage (device-resident leg, this rank) ----------------
+    # ---------------- roofline of the dominant kernel (device-resident leg, this rank) ----------------
+    # Stage times are CUDA-event intervals on the stream each stage runs on, averaged over the timed steps.
+    # The LM solve runs on its own stream CONCURRENTLY with blur_select + disparity (+ refine), so the stages
+    # do not add up to the step; the critical path is image_pyramid -> blur_select -> disparity ->
+    # depth_refine -> prepare, and the dominant kernel is taken among those.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -320,27 +324,50 @@ def main():
     stage_ms = {k: v / K for k, v in stage_acc.items()}
     npx = W * H
     pyr_px = sum((W >> l) * (H >> l) for l in range(LEVELS))
-    # algorithmic (compulsory) bytes per frame of each stage, DESIGN.md "Algorithmic bytes"
+    # algorithmic (compulsory) bytes per frame of each stage, DESIGN.md section 3
     alg_bytes = {
         "image_pyramid": 4 * (npx + pyr_px),
-        "blur_select": 2 * 8 * npx + npx + 8 * npx,          # blur L,R (read+write), val, zero-filled disp/dep
+        "blur_select": 8 * npx + 4 * npx + npx,              # blur R (read + write), gradient read of blur L, val
         "disparity": 17 * npx,                               # read L,R blur, val; write disp, dep
-        "depth_pyr_promote_prepare": 4 * (npx + pyr_px),
+        "depth_refine": 20 * 40960,                          # one pass of the slot state (11-15 passes run)
+        "depth_pyr_promote_prepare": 8 * pyr_px,             # point lists of a promoted keyframe: read img + depth
     }
-    dom = max(stage_ms, key=stage_ms.get)
-    roof = {"bound": "hbm", "kernel": dom, "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src, "traffic": None}
-    if dom in alg_bytes:
-        ach = alg_bytes[dom] * S / (stage_ms[dom] * 1e-3) / 1e9
-    else:
-        # iteration-bound stages (LM solve, depth refinement): L2-resident working set, latency bound;
-        # report the compulsory one-pass bytes so the fraction is an honest (small) number
-        one_pass = {"lm_solve": 4 * pyr_px + 48 * 40960, "depth_refine": 20 * 40960}[dom]
-        ach = one_pass * S / (stage_ms[dom] * 1e-3) / 1e9
-        roof["note"] = "iteration/latency bound stage: achieved = one compulsory pass of its inputs / stage time"
-    roof["achieved"] = ach
-    roof["frac"] = ach / hbm_peak
-    roof["stage_ms_per_step"] = stage_ms
-    roof["per_stage_gbs"] = {k: alg_bytes[k] * S / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}
+    critical = [k for k in stage_ms if k != "lm_solve"]
+    dom = max(critical, key=lambda k: stage_ms[k])
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")))
+        if prof.get("sequences_per_launch") == S and dom in prof.get("stage_dram_bytes", {}):
+            traffic = prof["stage_dram_bytes"][dom]
+    except Exception:
+        pass
+    ach = alg_bytes[dom] * S / (stage_ms[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": {"disparity": "k_quantize + k_disparity<true,1280>"}.get(dom, dom), "stage": dom,
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+            "peak_source": peak_src, "launch_ms": stage_ms[dom],
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * S,
+            "stage_ms_per_step": stage_ms,
+            "stages_overlap": "lm_solve runs on a second stream concurrently with blur_select/disparity/depth_refine",
+            "per_stage_gbs": {k: alg_bytes[k] * S / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}}
+    if dom == "disparity":
+        # the line search is bound by integer-multiply issue, not by HBM: 8 IMAD per (pixel, candidate) on the
+        # half-rate fmaheavy pipe (ncu: sm__pipe_fmaheavy_cycles_active).  Candidate evaluations of one frame are
+        # counted from the selection mask of a frame of the timed region (through the C-ABI).
+        try:
+            f_probe = 1 + Wm
+            rc_, _, _, val_ = ctx.select_pixels(frames_u8[f_probe, 0, 0].float().cpu().numpy(),
+                                                frames_u8[f_probe, 0, 1].float().cpu().numpy(), capi.default_depth_params())
+            ys, xs = np.nonzero(val_)
+            evals = float(np.maximum(xs - 4, 0).sum())
+            sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_evals = sm * 4 * 16 * clk / 8.0              # 16 IMAD lanes per scheduler per clock, 8 IMAD per evaluation
+            ach_evals = evals * S / (stage_ms[dom] * 1e-3)
+            roof["issue_roofline"] = {"bound": "imad (fmaheavy pipe)", "unit": "candidate evaluations/s",
+                                      "evaluations_per_frame": evals, "achieved": ach_evals, "peak": peak_evals,
+                                      "frac": ach_evals / peak_evals}
+        except Exception as e:  # the probe is informational
+            roof["issue_roofline"] = {"error": str(e)}
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None

@@ -100,8 +100,10 @@ struct LmLists {
 };
 size_t lm_lists_bytes(const PyrGeom& g, int batch, LmLists* layout);  // fills offsets, returns bytes needed
 void lm_lists_bind(LmLists* L, void* mem, const PyrGeom& g, int batch);
+// dep_from_l0: dep_pyr holds only level 0 of each sequence's depth pyramid (levels 1.. are read through the
+// odd-pixel subsampling rule)
 void launch_lm_prepare(odo_ctx* c, const float* img_pyr, int64_t istride, const float* dep_pyr, int64_t dstride,
-                       const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active);
+                       const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active, int dep_from_l0 = 0);
 
 struct LmLevelOut {      // sums of the last evaluation at a level (test hook / stats)
   double H[21];

@@ -7,6 +7,7 @@
 // (run_odometry_kitti_offline.cpp:254-270) is taken on the device.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -171,18 +172,6 @@ __global__ void k_track_finalize(SeqState* st, const odo_depth_stats* ds, int* p
     for (int i = 0; i < 16; i++) s.kf_pose_abs[i] = s.cur_pose[i];
 }
 
-__global__ void k_promote_copy(const float* __restrict__ src, float* __restrict__ dst, int64_t n,
-                               const int* __restrict__ flags) {
-  if (!flags[blockIdx.y]) return;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int64_t o = (int64_t)blockIdx.y * n;
-  if (i + 3 < n) {
-    *reinterpret_cast<float4*>(dst + o + i) = *reinterpret_cast<const float4*>(src + o + i);
-  } else {
-    for (int64_t k = i; k < n; k++) dst[o + k] = src[o + k];
-  }
-}
-
 }  // namespace
 
 struct odo_tracker {
@@ -198,11 +187,18 @@ struct odo_tracker {
   float *in_left[2] = {nullptr, nullptr}, *in_right[2] = {nullptr, nullptr};
   uint8_t* in_u8[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
+  // the LM solve of a frame (latency bound: a chain of up to 90 dependent iterations that leaves most issue
+  // slots idle) and its depth pipeline (throughput bound) are independent until the keyframe decision:
+  // they run concurrently, the solve on this second stream
+  cudaStream_t lm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_lm_done = nullptr;
+  cudaEvent_t ev_lm[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // per slot: solve begin / end on the LM stream
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // copy stream: the slot's frame is on the device
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr}; // compute stream: the last kernel reading the slot's frame is queued
   cudaEvent_t ev_done[2] = {nullptr, nullptr};     // compute stream: the slot's results are in h_state[slot]
   int64_t n_enqueued = 0, n_collected = 0;
-  float *cur_img = nullptr, *kf_img = nullptr, *cur_dep = nullptr, *kf_dep = nullptr;
+  bool lm_ran[2] = {false, false};
+  float *cur_img = nullptr, *cur_dep = nullptr;
   DepthWork dw;
   LmLists lists;
   LmWork lmw;
@@ -234,12 +230,24 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
   launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n);
   cudaEventRecord(ev[1], c->stream);
+  t->lm_ran[slot] = !first;
   if (!first) {
-    // Solve against the keyframe (:215)
-    if (launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1) != 0)
-      return -1;
-    k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
-    c->launches++;
+    // Solve against the keyframe (:215), forked onto the LM stream
+    cudaStream_t main_stream = c->stream;
+    cudaEventRecord(t->ev_fork, main_stream);
+    cudaStreamWaitEvent(t->lm_stream, t->ev_fork, 0);
+    c->stream = t->lm_stream;
+    cudaEventRecord(t->ev_lm[slot][0], t->lm_stream);
+    const int rc = launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n,
+                                   t->G_lm, -1);
+    if (rc == 0) {
+      k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
+      c->launches++;
+    }
+    cudaEventRecord(t->ev_lm[slot][1], t->lm_stream);
+    cudaEventRecord(t->ev_lm_done, t->lm_stream);
+    c->stream = main_stream;
+    if (rc != 0) return -1;
   }
   cudaEventRecord(ev[2], c->stream);
   // ComputeDepth on every frame (:226-229), then DepthPyramid (:252)
@@ -253,17 +261,15 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(ev[5], c->stream);
   cudaEventRecord(t->ev_consumed[slot], c->stream);  // nothing after this point reads the input frame
-  launch_depth_pyramid(c, t->dw.dep, t->dw.dep_stride, t->cur_dep, t->pyr_stride, t->g, 0, n);
+  // DepthPyramid(levels, dep, false) (:252) is a pure subsampling of the refined map: the point lists below read
+  // it through level 0, nothing else in the loop looks at levels 1.., so it is not materialised
+  if (!first) cudaStreamWaitEvent(c->stream, t->ev_lm_done, 0);  // join: the keyframe rule needs the pose
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
-  // keyframe promotion (:258-265): the new keyframe's pyramids and LM point lists
-  {
-    const int64_t nf = t->g.total;
-    dim3 grid((unsigned)((nf / 4 + 255) / 256 + 1), n);
-    k_promote_copy<<<grid, 256, 0, c->stream>>>(t->cur_img, t->kf_img, t->pyr_stride, t->promote);
-    k_promote_copy<<<grid, 256, 0, c->stream>>>(t->cur_dep, t->kf_dep, t->pyr_stride, t->promote);
-    c->launches += 3;
-  }
-  launch_lm_prepare(c, t->kf_img, t->pyr_stride, t->kf_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote);
+  c->launches++;
+  // keyframe promotion (:258-265): the only thing Solve needs from a keyframe are its point lists, built
+  // straight from the promoted frame's pyramids (no copy of the pyramids themselves)
+  launch_lm_prepare(c, t->cur_img, t->pyr_stride, t->cur_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote,
+                    /*dep_from_l0=*/1);
   t->lm.lambda = 0.01f;  // Reset(pose, 0.01f)
   cudaEventRecord(ev[6], c->stream);
   ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state[slot], t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -279,6 +285,8 @@ static int tracker_finish(odo_tracker* t, int slot, float* pose_abs, float* pose
   const int n = t->n;
   ODO_CUDA_OK(c, cudaEventSynchronize(t->ev_done[slot]));
   for (int i = 0; i < ODO_N_STAGES; i++) cudaEventElapsedTime(&t->stage_ms[i], t->ev[slot][i], t->ev[slot][i + 1]);
+  // the solve runs on its own stream, concurrently with stages 2-4
+  if (t->lm_ran[slot]) cudaEventElapsedTime(&t->stage_ms[1], t->ev_lm[slot][0], t->ev_lm[slot][1]);
   int rc = 0;
   for (int b = 0; b < n; b++) {
     const SeqState& s = t->h_state[slot][b];
@@ -348,7 +356,10 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   t->npx = (int64_t)w * h;
   t->pyr_stride = (t->g.total + 3) / 4 * 4;
   // CTAs per sequence for the persistent LM kernel: fill the SMs across the batch
-  int G = lm_max_ctas(c) / n_seq;
+  // The solve overlaps the depth pipeline (tracker_launch).  With many sequences it is off the critical path
+  // and should leave the SMs to the throughput-bound depth kernels: about half an SM-load of CTAs in total;
+  // a single sequence gets enough CTAs to spread level 0.
+  int G = c->sm_count / (2 * n_seq);
   const int gmax = (int)((t->npx + 16383) / 16384);
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
@@ -365,7 +376,7 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   const size_t rs_b = al256(sizeof(LmResult) * n_seq);
   const size_t st_b = al256(sizeof(SeqState) * n_seq);
   const size_t pf_b = al256(sizeof(int) * n_seq);
-  bytes = (in_b * 2 + u8_b) * 2 + pyr_b * 4 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
+  bytes = (in_b * 2 + u8_b) * 2 + pyr_b * 2 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
   if (cudaMalloc(&t->mem, bytes) != cudaSuccess) {
     c->err = "tracker: cudaMalloc failed";
     delete t;
@@ -379,9 +390,7 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
     t->in_u8[k] = (uint8_t*)p; p += u8_b;
   }
   t->cur_img = (float*)p; p += pyr_b;
-  t->kf_img = (float*)p; p += pyr_b;
   t->cur_dep = (float*)p; p += pyr_b;
-  t->kf_dep = (float*)p; p += pyr_b;
   depth_work_bind(&t->dw, p, w, h, n_seq, false); p += dw_b;
   // level 0 of the image pyramid IS GaussianBlur(left) and level 0 of the depth pyramid IS the refined
   // inverse depth: alias them instead of computing / copying them twice; the disparity map is a display
@@ -405,6 +414,15 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   }
   t->h_state[1] = t->h_state[0] + n_seq;
   cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&t->lm_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming);
+  for (int k = 0; k < 2; k++)
+    for (int i = 0; i < 2; i++) cudaEventCreate(&t->ev_lm[k][i]);
+  if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // experiment knob
+    const int g = std::atoi(e);
+    if (g >= 1 && g <= t->G_lm) t->G_lm = g;
+  }
   for (int k = 0; k < 2; k++) {
     for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[k][i]);
     cudaEventCreateWithFlags(&t->ev_copied[k], cudaEventDisableTiming);
@@ -426,6 +444,15 @@ void odo_tracker_destroy(odo_tracker* t) {
     cudaStreamSynchronize(t->copy_stream);
     cudaStreamDestroy(t->copy_stream);
   }
+  if (t->lm_stream) {
+    cudaStreamSynchronize(t->lm_stream);
+    cudaStreamDestroy(t->lm_stream);
+  }
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_lm_done) cudaEventDestroy(t->ev_lm_done);
+  for (int k = 0; k < 2; k++)
+    for (int i = 0; i < 2; i++)
+      if (t->ev_lm[k][i]) cudaEventDestroy(t->ev_lm[k][i]);
   cudaFree(t->mem);
   cudaFreeHost(t->h_state[0]);
   for (int k = 0; k < 2; k++) {
