@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per GPU (batch of one step)")
+    ap.add_argument("--streams", type=int, default=1, help="independent trackers (contexts/streams) per GPU sharing --seqs")
     ap.add_argument("--cpu-seqs", type=int, default=2, help="sequences of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -55,7 +56,7 @@ def config_dict(args, extra=None):
         "lm": "lambda 0.01, precision 0.995, iters {10,20,30,30}, Huber 28",
         "depth": "grad_th 8, ssd_th 900, photo_th 15, 0.1-30 m, 50 iters, boundary 4",
         "trajectory": "0.8 m/frame forward, yaw 0.4deg*sin(2*pi*t/100), seeds 20190113+sequence_id",
-        "parallelism": f"sequence sharding x{args.gpus}, no collective",
+        "parallelism": f"sequence sharding x{args.gpus} GPUs x{args.streams} trackers per GPU, no collective",
         "l2": "each step reads a fresh batch of frames (S*3.7 MB > 126 MB L2 for S >= 34); no explicit flush",
     }
     if extra:
@@ -209,6 +210,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     S, K, Wm = args.seqs, args.steps, args.warmup
@@ -217,7 +219,17 @@ def main():
     seq_ids = shard.shard_sequences(world * S, world, rank)
     frames_u8 = render_sequences(seq_ids, n_frames, dev)                # [F][S][2][H][W] u8 on device
     stream = torch.cuda.current_stream(dev)
-    ctx = capi.Context(local_rank, stream.cuda_stream)
+    # T trackers per GPU, each with its own context (= its own CUDA streams) and S/T of the sequences.  A
+    # frame is a dependent chain of kernels, some throughput bound (disparity search), some latency bound
+    # (the LM and refinement iteration loops); independent trackers interleave on the GPU so that one
+    # tracker's latency-bound stages run under another's throughput-bound ones.  Pure orchestration of the
+    # same C-ABI calls: sequences are sharded over streams exactly as they are over GPUs.
+    T = max(1, min(args.streams, S))
+    while S % T:
+        T -= 1
+    St = S // T
+    ctxs = [capi.Context(local_rank) for _ in range(T)]
+    ctx = ctxs[0]
 
     def barrier():
         shard.barrier(dev)
@@ -225,88 +237,99 @@ def main():
     def max_over_ranks(ms):
         return shard.max_over_ranks(ms, dev)
 
+    def launch_total():
+        return sum(c.launch_count() for c in ctxs)
+
+    def run_pipelined(trks, enqueue, f0, f1, on_result=None):
+        """Two frames in flight per tracker: frame f+1 is enqueued (copies + kernels) before frame f is
+        collected; every frame's poses are read back."""
+        for i, t in enumerate(trks):
+            enqueue(t, i, f0)
+        for f in range(f0, f1):
+            for i, t in enumerate(trks):
+                if f + 1 < f1:
+                    enqueue(t, i, f + 1)
+                res = t.collect()
+                assert res[0] == 0, "tracking failed"
+                if on_result:
+                    on_result(t, res)
+
+    def timed(fn):
+        """Device time of fn() between two idle points: e0 is recorded with the GPU idle, e1 after the host
+        has collected the last result of every tracker (nothing is left running)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---------------- leg 1: inputs resident in HBM ----------------
     frames_f32 = frames_u8.to(torch.float32)                            # [F][S][2][H][W] float32 on device
     left_dev = frames_f32[:, :, 0].contiguous()
     right_dev = frames_f32[:, :, 1].contiguous()
     del frames_f32
-    trk = capi.Tracker(ctx, W, H, LEVELS, S)
-    for f in range(0, 1 + Wm):
-        rc, *_ = trk.step_dev(left_dev[f].data_ptr(), right_dev[f].data_ptr())
+    trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
+
+    def enq_dev(t, i, f):
+        t.enqueue_dev(left_dev[f, i * St].data_ptr(), right_dev[f, i * St].data_ptr())
+
+    run_pipelined(trks, enq_dev, 0, 1 + Wm)
     sampler = ClockSampler(local_rank)
-    stage_acc = {}
-    launches0 = ctx.launch_count()
-    barrier()
+    stage_acc, tally = {}, {"kf": 0, "ok": True}
+
+    def on_result(t, res):
+        rc, pa, pk, kf, st = res
+        tally["kf"] += int(kf.sum())
+        tally["ok"] &= bool((st == 0).all())
+        for k, v in t.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / T
+
+    launches0 = launch_total()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    n_kf = 0
-    for f in range(1 + Wm, n_frames):
-        rc, pa, pk, kf, st = trk.step_dev(left_dev[f].data_ptr(), right_dev[f].data_ptr())
-        n_kf += int(kf.sum())
-        for k, v in trk.stage_ms().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-    e1.record(stream)
-    barrier()
+    ms_total = timed(lambda: run_pipelined(trks, enq_dev, 1 + Wm, n_frames, on_result))
     clocks = sampler.result()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.launch_count() - launches0
+    launches = launch_total() - launches0
     value = world * S * K / (ms_total * 1e-3)
-    status_ok = bool((st == 0).all())
-    trk.close()
+    n_kf, status_ok = tally["kf"], tally["ok"]
+    for t in trks:
+        t.close()
     del left_dev, right_dev
 
     # ---------------- leg 2: end to end through the C-ABI with host buffers ----------------
     e2e = None
     if not args.no_e2e:
         host = frames_u8.to(torch.float32).cpu().pin_memory()           # [F][S][2][H][W] pinned CV_32F frames
-        trk = capi.Tracker(ctx, W, H, LEVELS, S)
+        trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
 
-        def ptrs(f, eye):
-            base = host[f, :, eye]
-            return [base[s].data_ptr() for s in range(S)]
+        def enq_host(t, i, f):
+            base = host[f, i * St:(i + 1) * St]
+            t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)])
 
-        def pipelined(f0, f1, p, u8=False):
-            """odo_tracker_enqueue / odo_tracker_collect: the H2D copy of frame f+1 is in flight while
-            the kernels of frame f run; every frame's poses are read back before the next collect."""
-            trk.enqueue_ptrs(p(f0, 0), p(f0, 1), u8=u8)
-            for f in range(f0, f1):
-                if f + 1 < f1:
-                    trk.enqueue_ptrs(p(f + 1, 0), p(f + 1, 1), u8=u8)
-                rc, *_ = trk.collect()
-                assert rc == 0
-
-        pipelined(0, 1 + Wm, ptrs)
-        barrier()
-        e0.record(stream)
-        pipelined(1 + Wm, n_frames, ptrs)
-        e1.record(stream)
-        barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        run_pipelined(trks, enq_host, 0, 1 + Wm)
+        ms_e2e = timed(lambda: run_pipelined(trks, enq_host, 1 + Wm, n_frames))
         e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": S * 2 * W * H * 4, "d2h_bytes_per_step": S * 240,
                "ms_per_step": ms_e2e / K, "host_buffers": "pinned float32 (CV_32F), one pointer per image",
-               "api": "odo_tracker_enqueue + odo_tracker_collect (two frames in flight: the copy of frame f+1 "
-                      "overlaps the kernels of frame f; every frame's poses are read back)"}
-        trk.close()
+               "api": "odo_tracker_enqueue + odo_tracker_collect (two frames in flight per tracker: the copy of "
+                      "frame f+1 overlaps the kernels of frame f; every frame's poses are read back)"}
+        for t in trks:
+            t.close()
         # fused u8 ingest (row f2 of SURVEY 8f): same call with the frames as the PNG decoder leaves them
         host8 = frames_u8.cpu().pin_memory()
-        trk = capi.Tracker(ctx, W, H, LEVELS, S)
+        trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
 
-        def ptrs8(f, eye):
-            base = host8[f, :, eye]
-            return [base[s].data_ptr() for s in range(S)]
+        def enq_host8(t, i, f):
+            base = host8[f, i * St:(i + 1) * St]
+            t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)], u8=True)
 
-        pipelined(0, 1 + Wm, ptrs8, u8=True)
-        barrier()
-        e0.record(stream)
-        pipelined(1 + Wm, n_frames, ptrs8, u8=True)
-        e1.record(stream)
-        barrier()
-        ms_u8 = max_over_ranks(e0.elapsed_time(e1))
+        run_pipelined(trks, enq_host8, 0, 1 + Wm)
+        ms_u8 = timed(lambda: run_pipelined(trks, enq_host8, 1 + Wm, n_frames))
         e2e["u8_ingest"] = {"value": world * S * K / (ms_u8 * 1e-3), "unit": "frames/s",
                             "h2d_bytes_per_step": S * 2 * W * H}
-        trk.close()
+        for t in trks:
+            t.close()
         del host, host8
 
     # ---------------- roofline of the dominant kernel (device-resident leg, this rank) ----------------
@@ -337,18 +360,19 @@ def main():
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")))
-        if prof.get("sequences_per_launch") == S and dom in prof.get("stage_dram_bytes", {}):
+        if prof.get("sequences_per_launch") == St and dom in prof.get("stage_dram_bytes", {}):
             traffic = prof["stage_dram_bytes"][dom]
     except Exception:
         pass
-    ach = alg_bytes[dom] * S / (stage_ms[dom] * 1e-3) / 1e9
+    # a launch of the dominant kernel covers the St sequences of one tracker
+    ach = alg_bytes[dom] * St / (stage_ms[dom] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": {"disparity": "k_quantize + k_disparity<true,1280>"}.get(dom, dom), "stage": dom,
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
             "peak_source": peak_src, "launch_ms": stage_ms[dom],
-            "algorithmic_bytes_per_launch": alg_bytes[dom] * S,
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * St, "sequences_per_launch": St,
             "stage_ms_per_step": stage_ms,
             "stages_overlap": "lm_solve runs on a second stream concurrently with blur_select/disparity/depth_refine",
-            "per_stage_gbs": {k: alg_bytes[k] * S / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}}
+            "per_stage_gbs": {k: alg_bytes[k] * St / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}}
     if dom == "disparity":
         # the line search is bound by integer-multiply issue, not by HBM: 8 IMAD per (pixel, candidate) on the
         # half-rate fmaheavy pipe (ncu: sm__pipe_fmaheavy_cycles_active).  Candidate evaluations of one frame are
@@ -362,7 +386,7 @@ def main():
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
             clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
             peak_evals = sm * 4 * 16 * clk / 8.0              # 16 IMAD lanes per scheduler per clock, 8 IMAD per evaluation
-            ach_evals = evals * S / (stage_ms[dom] * 1e-3)
+            ach_evals = evals * St / (stage_ms[dom] * 1e-3)
             roof["issue_roofline"] = {"bound": "imad (fmaheavy pipe)", "unit": "candidate evaluations/s",
                                       "evaluations_per_frame": evals, "achieved": ach_evals, "peak": peak_evals,
                                       "frac": ach_evals / peak_evals}
@@ -389,7 +413,8 @@ def main():
             "disparity_mpix_per_s": (npx * S / 1e6) / ((stage_ms["blur_select"] + stage_ms["disparity"] + stage_ms["depth_refine"]) * 1e-3),
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -163,6 +163,8 @@ int  odo_tracker_collect(odo_tracker* t, float* pose_abs, float* pose_kf, int* i
  * contiguous [n_seq][h][w] float32 block per eye. */
 int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev,
                           float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
+/* same without waiting (pair with odo_tracker_collect); the device buffers must stay untouched until then */
+int  odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* right_dev);
 
 /* device time of the stages of the last step, in ms (CUDA events on the context's stream):
  * 0 image pyramid, 1 LM solve + pose update, 2 blur + selection, 3 disparity search,

@@ -52,7 +52,7 @@ EXPORTS = [
     "odo_compute_depth", "odo_select_pixels", "odo_disparity_search", "odo_depth_optimize",
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
     "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev", "odo_tracker_stage_ms",
-    "odo_tracker_enqueue", "odo_tracker_enqueue_u8", "odo_tracker_collect",
+    "odo_tracker_enqueue", "odo_tracker_enqueue_u8", "odo_tracker_enqueue_dev", "odo_tracker_collect",
 ]
 STAGES = ["image_pyramid", "lm_solve", "blur_select", "disparity", "depth_refine", "depth_pyr_promote_prepare"]
 
@@ -299,6 +299,10 @@ class Tracker:
         la, ra = arr_t(*left_ptrs), arr_t(*right_ptrs)
         fn = lib().odo_tracker_enqueue_u8 if u8 else lib().odo_tracker_enqueue
         if fn(self.h, la, ra) != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def enqueue_dev(self, left_dev_ptr, right_dev_ptr):
+        if lib().odo_tracker_enqueue_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr)) != 0:
             raise OdoError(self.ctx.last_error())
 
     def collect(self):

@@ -75,11 +75,21 @@ struct odo_pyr {
 // ---- pyramid.cu ----------------------------------------------------------------------------------
 // All launchers are batched: element b of the batch lives at base + b * stride (in elements).
 void launch_u8_to_f32(odo_ctx* c, const uint8_t* src, float* dst, int64_t n);
-void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch);
+// optional second output of the 3x3 blur: q = 16 * value as u16 (rows of `pitch` elements, `stride` elements
+// per sequence) for the exact integer disparity search; exact[b] is cleared when a value is not a multiple of
+// 1/16 in [0, 255].  plane == nullptr: no second output.
+struct QuantOut {
+  uint16_t* plane = nullptr;
+  int64_t stride = 0;
+  int pitch = 0;
+  int* exact = nullptr;
+};
+void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
+                  QuantOut q = QuantOut());
 void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
                     int dw, int dh, int batch);
 void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
-                          const PyrGeom& g, int smooth, int batch);
+                          const PyrGeom& g, int smooth, int batch, QuantOut q0 = QuantOut());
 void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,
                           const PyrGeom& g, int smooth, int batch);
 
@@ -154,12 +164,12 @@ struct DepthWork {
   int cap;             // pixel-list capacity per sequence
   int64_t blurL_stride;  // elements between sequences in blurL (the tracker aliases level 0 of the image pyramid)
   int64_t dep_stride;    // elements between sequences in dep (the tracker aliases level 0 of the depth pyramid)
-  // exact integer path of the line search (depth.cu, k_quantize): q = 16 * blur as u16, pattern energy of
-  // every right candidate, and per sequence "both blurred images are multiples of 1/16 in [0, 255]"
+  // exact integer path of the line search (depth.cu, k_disparity): q = 16 * blur as u16 and, per sequence,
+  // "both blurred images are multiples of 1/16 in [0, 255]"
   uint16_t* qL;        // [batch][w*h]
   uint16_t* qR;
-  int* eR;             // [batch][w*h]
   int* exact;          // [batch]
+  int q_ready;         // qL / qR / exact were already produced by the blur kernels of this frame
   // raw (unblurred) right image as u8 for the refinement (depth.cu, k_refine): rawR8 == nullptr makes
   // launch_depth_refine build it into rawR8_own from the float frame; a caller that already has the u8
   // frame on the device points rawR8 at it and sets raw_exact[b] = 1 itself
@@ -173,8 +183,10 @@ size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)
 void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debug);
 // blur_left_done: d.blurL already holds GaussianBlur(L) (image pyramid level 0 of the same frame)
+QuantOut depth_quant_left(const DepthWork& d, const odo_depth_params& p, int w, int h);  // q output of the left blur
+void depth_quant_reset(odo_ctx* c, const DepthWork& d, int batch);  // exact[b] = 1 before the frame's blurs
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
-                   const odo_depth_params& p, DepthWork d, int batch, bool blur_left_done = false);
+                   const odo_depth_params& p, DepthWork& d, int batch, bool blur_left_done = false);
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch);
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch);

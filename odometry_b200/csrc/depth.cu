@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
 //    accept test are reproduced bit for bit by integer arithmetic on 256*SSD = El + Er - 2*cross:
 //    El / Er are the pattern energies of the left pixel / right candidate, cross the 8-tap correlation.
 //    Per (pixel, candidate) that is 8 IMAD + compare/select instead of 8 FSUB + 8 FMUL + 7 FADD +
-//    compare/select, and Er is shared by the pixels of a group.  k_quantize builds q for both images,
-//    Er for the right one, and clears `exact` on any other value; such sequences take the fp32 path.
+//    compare/select, and Er is shared by the pixels of a group (computed once per row from the staged rows).
+//    The blur kernels emit q next to the float image (pyramid.cu, QuantOut; k_quantize for callers that bring
+//    their own blurred images) and clear `exact` on any other value; such sequences take the fp32 path.
 constexpr int kDispThreads = 128;
 constexpr int kDispWarps = kDispThreads / 32;
 constexpr int kDispP = 4;
@@ -181,18 +182,6 @@ __global__ void __launch_bounds__(256) k_quantize(int W, int H, DepthWork d) {
     bad = !(l16 >= 0.0f && l16 <= 4080.0f && l16 == rintf(l16) && r16 >= 0.0f && r16 <= 4080.0f && r16 == rintf(r16));
     d.qL[qo] = (uint16_t)(bad ? 0 : (int)l16);
     d.qR[qo] = (uint16_t)(bad ? 0 : (int)r16);
-    int e = 0;
-    if (x >= 2 && x < W - 2 && y >= 2 && y < H - 2) {
-      // pattern taps (:380-381): nn[x], n[x-1], c[x+2], c[x], c[x-2], p[x+1], p[x-1], pp[x]
-      const float t[8] = {__ldg(br + o + 2 * W), __ldg(br + o + W - 1), __ldg(br + o + 2), __ldg(br + o), __ldg(br + o - 2),
-                          __ldg(br + o - W + 1), __ldg(br + o - W - 1), __ldg(br + o - 2 * W)};
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int q = (int)__fmul_rn(t[k], 16.0f);  // garbage when not exact: the flag sends the search elsewhere
-        e += q * q;
-      }
-    }
-    d.eR[qo] = e;
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&d.exact[b], 0);
 }
@@ -272,10 +261,15 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
       uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(s_rows) + r * PITCH + 2 + v * 8);
       dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
     }
-    const int* esrc = d.eR + b * qpx + (int64_t)y * QP;
-    const int ne4 = (ncol + 3) >> 2;
-    for (int i = threadIdx.x; i < ne4; i += kDispThreads)
-      reinterpret_cast<int4*>(s_er)[i] = __ldg(reinterpret_cast<const int4*>(esrc) + i);
+    __syncthreads();
+    // pattern energy of every candidate column of this row (shared by all pixels of the row)
+    const uint16_t* c0 = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2;
+    for (int cx = bnd + threadIdx.x; cx < xlast; cx += kDispThreads) {
+      const uint16_t* c = c0 + cx;
+      const int t0 = c[2 * PITCH], t1 = c[PITCH - 1], t2 = c[2], t3 = c[0], t4 = c[-2], t5 = c[-PITCH + 1],
+                t6 = c[-PITCH - 1], t7 = c[-2 * PITCH];
+      s_er[cx] = t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6 + t7 * t7;
+    }
   } else {
     const float* src = d.blurR + b * npx + (int64_t)(y - 2) * W;
     for (int r = 0; r < 5; r++)
@@ -741,7 +735,7 @@ size_t depth_work_bytes(int w, int h, int batch, bool debug) {
   bytes += al((size_t)batch * 6 * kGridBlocks * kSelMax * 4);   // refinement state: 16 + 8 bytes per slot
   bytes += al(npx) + al((size_t)batch * 4) + 256;               // raw right image as u8, raw_exact, dbg
   const size_t qpx = (size_t)q_pitch(w) * h * batch + 16;  // +16: the staging reads whole 16-byte vectors
-  bytes += al(qpx * 2) * 2 + al(qpx * 4) + al((size_t)batch * 4);  // qL, qR, eR, exact
+  bytes += al(qpx * 2) * 2 + al((size_t)batch * 4);  // qL, qR, exact
   return bytes;
 }
 
@@ -769,8 +763,8 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   const size_t qpx = (size_t)q_pitch(w) * h * batch + 16;
   d->qL = (uint16_t*)p; p += al(qpx * 2);
   d->qR = (uint16_t*)p; p += al(qpx * 2);
-  d->eR = (int*)p; p += al(qpx * 4);
   d->exact = (int*)p; p += al((size_t)batch * 4);
+  d->q_ready = 0;
   d->rawR8_own = (uint8_t*)p; p += al(npx);
   d->raw_exact = (int*)p; p += al((size_t)batch * 4);
   d->dbg = (long long*)p;
@@ -781,12 +775,41 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->dep_stride = (int64_t)w * h;
 }
 
+static int q_eligible_for(const DepthWork& d, const odo_depth_params& p) {
+  // exact integer path (see k_disparity); min_ssd (a test-hook output) is defined by the fp32 path
+  return (d.qL && !d.min_ssd && p.ssd_th < 65536.0f) ? 1 : 0;
+}
+
+QuantOut depth_quant_left(const DepthWork& d, const odo_depth_params& p, int w, int h) {
+  QuantOut q;
+  if (q_eligible_for(d, p)) {
+    q.plane = d.qL;
+    q.pitch = q_pitch(w);
+    q.stride = (int64_t)q.pitch * h;
+    q.exact = d.exact;
+  }
+  return q;
+}
+
+void depth_quant_reset(odo_ctx* c, const DepthWork& d, int batch) {
+  if (d.exact) cudaMemsetAsync(d.exact, 0xff, sizeof(int) * batch, c->stream);
+}
+
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
-                   const odo_depth_params& p, DepthWork d, int batch, bool blur_left_done) {
+                   const odo_depth_params& p, DepthWork& d, int batch, bool blur_left_done) {
   const size_t npx = (size_t)w * h;
-  // cv::GaussianBlur on both images, :255-257 ; outputs zero-filled (quirk Q6)
-  if (!blur_left_done) launch_blur3(c, L, stride, d.blurL, d.blurL_stride, w, h, batch);
-  launch_blur3(c, R, stride, d.blurR, (int64_t)npx, w, h, batch);
+  // cv::GaussianBlur on both images, :255-257 (with q = 16 * blur as a second output when the integer line
+  // search may run); outputs zero-filled (quirk Q6).  blur_left_done: the caller blurred the left image (image
+  // pyramid level 0) and, if it wanted the integer path, reset `exact` and passed depth_quant_left() there.
+  const int qe = q_eligible_for(d, p);
+  QuantOut ql = depth_quant_left(d, p, w, h), qr = ql;
+  qr.plane = qe ? d.qR : nullptr;
+  if (!blur_left_done) {
+    if (qe) depth_quant_reset(c, d, batch);
+    launch_blur3(c, L, stride, d.blurL, d.blurL_stride, w, h, batch, ql);
+  }
+  launch_blur3(c, R, stride, d.blurR, (int64_t)npx, w, h, batch, qr);
+  d.q_ready = qe;
   cudaMemsetAsync(d.val, 0, npx * batch, c->stream);
   if (d.disp) cudaMemsetAsync(d.disp, 0, npx * batch * 4, c->stream);
   if (d.dep_stride == (int64_t)npx) cudaMemsetAsync(d.dep, 0, npx * batch * 4, c->stream);
@@ -814,9 +837,8 @@ static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params&
 
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch) {
   if (h - 2 * p.boundary <= 0 || p.boundary < 2) return;
-  // exact integer path (see k_quantize); min_ssd (a test-hook output) is defined by the fp32 path
-  const int q_eligible = (d.qL && !d.min_ssd && p.ssd_th < 65536.0f) ? 1 : 0;
-  if (q_eligible) {
+  const int q_eligible = q_eligible_for(d, p);
+  if (q_eligible && !d.q_ready) {  // blurred images brought by the caller: quantise them here
     cudaMemsetAsync(d.exact, 0xff, sizeof(int) * batch, c->stream);
     dim3 grid((w + 31) / 32, (h + 7) / 8, batch), block(32, 8);
     k_quantize<<<grid, block, 0, c->stream>>>(w, h, d);

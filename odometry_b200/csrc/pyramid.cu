@@ -40,28 +40,67 @@ __device__ __forceinline__ float tap121(float a, float b, float c) {
 }
 
 // cv::GaussianBlur(src, dst, Size(3,3), 0), CV_32F, BORDER_REFLECT_101.
-// Each thread produces kBlurRows vertically adjacent outputs of one column: the horizontal pass of a
-// source row is computed once and reused by the three output rows it feeds (18 coalesced loads per 4
-// outputs instead of 36).
-constexpr int kBlurRows = 4;
-__global__ void __launch_bounds__(256) k_blur3(const float* __restrict__ src, int64_t sstride,
-                                               float* __restrict__ dst, int64_t dstride, int w, int h) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y0 = (blockIdx.y * 8 + threadIdx.y) * kBlurRows;
-  if (x >= w || y0 >= h) return;
-  const float* s = src + (int64_t)blockIdx.z * sstride;
-  float* d = dst + (int64_t)blockIdx.z * dstride;
-  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  float t[kBlurRows + 2];
-#pragma unroll
-  for (int k = 0; k < kBlurRows + 2; k++) {
-    const int yy = reflect101(min(y0 - 1 + k, h), h);  // rows past the last output are never used
-    const float* r = s + (int64_t)yy * w;
-    t[k] = tap121(__ldg(r + xm), __ldg(r + x), __ldg(r + xp));
+// One thread owns one column of a strip of kBlurRows output rows and walks down it: the horizontal pass of a
+// source row is computed once (3 coalesced loads, served by L1 for the two neighbours) and feeds the three
+// output rows it belongs to through a rolling window, with running row pointers instead of per-row index
+// arithmetic -- about 20 instructions per output pixel, so the kernel is bound by HBM, not by issue.
+// Optionally the blurred value is also emitted as q = 16 * v in a u16 plane for the exact integer disparity
+// search (depth.cu): a value that is not a multiple of 1/16 in [0, 255] clears the sequence's `exact` flag.
+constexpr int kBlurRows = 16;
+
+__device__ __forceinline__ float blur_row(const float* __restrict__ p, int dm, int dp) {
+  // horizontal pass at the column p points to; dm / dp are the (reflected) neighbour offsets, -1 / +1 inside
+  return tap121(__ldg(p + dm), __ldg(p), __ldg(p + dp));
+}
+
+__device__ __forceinline__ bool quant_store(uint16_t* q, float v) {
+  // q = 16 * v when that is an integer in [0, 4080]; returns false (and stores 0) otherwise
+  const float v16 = __fmul_rn(v, 16.0f);
+  const int qi = __float2int_rn(v16);
+  const bool ok = (unsigned)qi <= 4080u && (float)qi == v16;
+  *q = (uint16_t)(ok ? qi : 0);
+  return ok;
+}
+
+template <bool QOUT>
+__global__ void __launch_bounds__(128) k_blur3(const float* __restrict__ src, int64_t sstride,
+                                               float* __restrict__ dst, int64_t dstride, int w, int h, QuantOut q) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y0 = blockIdx.y * kBlurRows;
+  bool bad = false;
+  if (x < w) {
+    const float* s = src + (int64_t)blockIdx.z * sstride + x;
+    float* d = dst + (int64_t)blockIdx.z * dstride + (int64_t)y0 * w + x;
+    uint16_t* qd = QOUT ? q.plane + (int64_t)blockIdx.z * q.stride + (int64_t)y0 * q.pitch + x : nullptr;
+    const int dm = reflect101(x - 1, w) - x, dp = reflect101(x + 1, w) - x;
+    const int y1 = min(y0 + kBlurRows, h);
+    float t0 = blur_row(s + (int64_t)reflect101(y0 - 1, h) * w, dm, dp);
+    const float* r = s + (int64_t)y0 * w;
+    float t1 = blur_row(r, dm, dp);
+    // rows whose successor is inside the image: the source pointer just advances
+    const int ym = min(y1, h - 1);
+#pragma unroll 4
+    for (int y = y0; y < ym; y++) {
+      r += w;
+      const float t2 = blur_row(r, dm, dp);
+      const float v = tap121(t0, t1, t2);
+      *d = v;
+      d += w;
+      if (QOUT) {
+        bad |= !quant_store(qd, v);
+        qd += q.pitch;
+      }
+      t0 = t1;
+      t1 = t2;
+    }
+    if (y1 == h && ym >= y0) {  // last image row: its successor is the mirror image (row h - 2)
+      const float t2 = blur_row(s + (int64_t)reflect101(h, h) * w, dm, dp);
+      const float v = tap121(t0, t1, t2);
+      *d = v;
+      if (QOUT) bad |= !quant_store(qd, v);
+    }
   }
-#pragma unroll
-  for (int k = 0; k < kBlurRows; k++)
-    if (y0 + k < h) d[(int64_t)(y0 + k) * w + x] = tap121(t[k], t[k + 1], t[k + 2]);
+  if (QOUT && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&q.exact[blockIdx.z], 0);
 }
 
 // horizontal 1-4-6-4-1 of one source row at even column 2x (unscaled)
@@ -74,30 +113,40 @@ __device__ __forceinline__ float hrow5(const float* __restrict__ r, int i0, int 
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s2, 6.f), __fmul_rn(__fadd_rn(s1, s3), 4.f)), s0), s4);
 }
 
-// cv::pyrDown(src, dst, Size(dw, dh)), CV_32F, BORDER_REFLECT_101 (OpenCV pyrDown_<FltCast<float,8>>)
-__global__ void __launch_bounds__(256) k_pyrdown(const float* __restrict__ src, int64_t sstride, int sw, int sh,
+// cv::pyrDown(src, dst, Size(dw, dh)), CV_32F, BORDER_REFLECT_101 (OpenCV pyrDown_<FltCast<float,8>>).
+// Same strip structure as k_blur3: a thread walks down one output column; consecutive output rows share three
+// of their five horizontally filtered source rows, so each step filters two new source rows.
+constexpr int kDownRows = 8;
+__global__ void __launch_bounds__(128) k_pyrdown(const float* __restrict__ src, int64_t sstride, int sw, int sh,
                                                  float* __restrict__ dst, int64_t dstride, int dw, int dh,
                                                  int hbody_end, int vbody_end) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  if (x >= dw || y >= dh) return;
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y0 = blockIdx.y * kDownRows;
+  if (x >= dw) return;
   const float* s = src + (int64_t)blockIdx.z * sstride;
+  float* d = dst + (int64_t)blockIdx.z * dstride + (int64_t)y0 * dw + x;
   const int i0 = reflect101(2 * x - 2, sw), i1 = reflect101(2 * x - 1, sw), i2 = reflect101(2 * x, sw),
             i3 = reflect101(2 * x + 1, sw), i4 = reflect101(2 * x + 2, sw);
   const bool hbody = (x >= 1) && (x < hbody_end);
-  float r[5];
-#pragma unroll
-  for (int k = 0; k < 5; k++) {
-    const int sy = reflect101(2 * y - 2 + k, sh);
-    r[k] = hrow5(s + (int64_t)sy * sw, i0, i1, i2, i3, i4, hbody);
+  const bool vbody = x < vbody_end;
+  const int y1 = min(y0 + kDownRows, dh);
+  float r0 = hrow5(s + (int64_t)reflect101(2 * y0 - 2, sh) * sw, i0, i1, i2, i3, i4, hbody);
+  float r1 = hrow5(s + (int64_t)reflect101(2 * y0 - 1, sh) * sw, i0, i1, i2, i3, i4, hbody);
+  float r2 = hrow5(s + (int64_t)reflect101(2 * y0, sh) * sw, i0, i1, i2, i3, i4, hbody);
+  for (int y = y0; y < y1; y++) {
+    const float r3 = hrow5(s + (int64_t)reflect101(2 * y + 1, sh) * sw, i0, i1, i2, i3, i4, hbody);
+    const float r4 = hrow5(s + (int64_t)reflect101(2 * y + 2, sh) * sw, i0, i1, i2, i3, i4, hbody);
+    float v;
+    if (vbody)  // v_muladd((r1 + r3) + r2, 4, (r0 + r4) + (r2 + r2))
+      v = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(r1, r3), r2), 4.f), __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)));
+    else  // row2*6 + (row1 + row3)*4 + row0 + row4
+      v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
+    *d = __fmul_rn(v, 1.f / 256.f);
+    d += dw;
+    r0 = r2;
+    r1 = r3;
+    r2 = r4;
   }
-  float v;
-  if (x < vbody_end)  // v_muladd((r1 + r3) + r2, 4, (r0 + r4) + (r2 + r2))
-    v = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(r[1], r[3]), r[2]), 4.f),
-                  __fadd_rn(__fadd_rn(r[0], r[4]), __fadd_rn(r[2], r[2])));
-  else  // row2*6 + (row1 + row3)*4 + row0 + row4
-    v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[2], 6.f), __fmul_rn(__fadd_rn(r[1], r[3]), 4.f)), r[0]), r[4]);
-  dst[(int64_t)blockIdx.z * dstride + (int64_t)y * dw + x] = __fmul_rn(v, 1.f / 256.f);
 }
 
 // batched contiguous copy, 4 x float4 per thread when both sides are 16-byte aligned
@@ -193,9 +242,11 @@ void launch_u8_to_f32(odo_ctx* c, const uint8_t* src, float* dst, int64_t n) {
   c->launches++;
 }
 
-void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch) {
-  dim3 grid((w + 31) / 32, (h + 8 * kBlurRows - 1) / (8 * kBlurRows), batch), block(32, 8);
-  k_blur3<<<grid, block, 0, c->stream>>>(src, sstride, dst, dstride, w, h);
+void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
+                  QuantOut q) {
+  dim3 grid((w + 127) / 128, (h + kBlurRows - 1) / kBlurRows, batch);
+  if (q.plane) k_blur3<true><<<grid, 128, 0, c->stream>>>(src, sstride, dst, dstride, w, h, q);
+  else k_blur3<false><<<grid, 128, 0, c->stream>>>(src, sstride, dst, dstride, w, h, q);
   c->launches++;
 }
 
@@ -207,16 +258,16 @@ void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int s
   if (width0 > dw) width0 = dw;
   const int hbody_end = (width0 > 1) ? 1 + lanes * ((width0 - 1) / lanes) : 1;
   const int vbody_end = lanes * (dw / lanes);
-  dim3 grid((dw + 31) / 32, (dh + 7) / 8, batch), block(32, 8);
-  k_pyrdown<<<grid, block, 0, c->stream>>>(src, sstride, sw, sh, dst, dstride, dw, dh, hbody_end, vbody_end);
+  dim3 grid((dw + 127) / 128, (dh + kDownRows - 1) / kDownRows, batch);
+  k_pyrdown<<<grid, 128, 0, c->stream>>>(src, sstride, sw, sh, dst, dstride, dw, dh, hbody_end, vbody_end);
   c->launches++;
 }
 
 void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
-                          const PyrGeom& g, int smooth, int batch) {
+                          const PyrGeom& g, int smooth, int batch, QuantOut q0) {
   const int64_t n0 = (int64_t)g.w[0] * g.h[0];
   if (smooth) {
-    launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch);
+    launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch, q0);
   } else {
     launch_copy_batched(c, img, istride, pyr, pstride, n0, batch);
   }

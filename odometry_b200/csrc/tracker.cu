@@ -228,7 +228,9 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   c->err.clear();
   cudaEventRecord(ev[0], c->stream);
   // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
-  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n);
+  // level 0 doubles as the blurred left image of the depth stage: emit its u16 copy for the integer line search
+  depth_quant_reset(c, t->dw, n);
+  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, depth_quant_left(t->dw, t->dp, t->w, t->h));
   cudaEventRecord(ev[1], c->stream);
   t->lm_ran[slot] = !first;
   if (!first) {
@@ -521,13 +523,24 @@ int odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8_
   return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
-int odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev, float* pose_abs,
-                         float* pose_kf, int* is_keyframe, int* status) {
-  if (!t || !left_dev || !right_dev || t->n_enqueued != t->n_collected) return -1;
-  ODO_CUDA_OK(t->c, cudaSetDevice(t->c->device));
+int odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* right_dev) {
+  if (!t || !left_dev || !right_dev) return -1;
+  odo_ctx* c = t->c;
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  if (t->n_enqueued - t->n_collected >= 2) {
+    c->err = "tracker: two frames are already in flight, collect one first";
+    return -1;
+  }
   const int slot = (int)(t->n_enqueued & 1);
   if (tracker_launch(t, left_dev, right_dev, slot) != 0) return -1;
   t->n_enqueued++;
+  return 0;
+}
+
+int odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev, float* pose_abs,
+                         float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || t->n_enqueued != t->n_collected) return -1;
+  if (odo_tracker_enqueue_dev(t, left_dev, right_dev) != 0) return -1;
   return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
@@ -599,6 +612,7 @@ int odo_disparity_search(odo_ctx* c, const float* blur_left, const float* blur_r
   else ODO_CUDA_OK(c, cudaMemsetAsync(dw.min_ssd, 0, npx * 4, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(dw.stats, 0, sizeof(odo_depth_stats), c->stream));
   // the kernel visits every pixel the reference's loops visit: y, x in [boundary, size - boundary), val != 0 (:346-354)
+  dw.q_ready = 0;  // the caller's blurred images have not been quantised
   launch_disparity(c, w, h, *p, dw, 1);
   if (disp) ODO_CUDA_OK(c, cudaMemcpyAsync(disp, dw.disp, npx * 4, cudaMemcpyDeviceToHost, c->stream));
   if (dep) ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
