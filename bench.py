@@ -11,8 +11,9 @@ own S sequences (sharding of independent sequences, no data-path collective => w
   e2e   : frames/s through the reference-facing C-ABI call with HOST buffers (CV_32F images in
           pinned memory, H2D of the step's frames and D2H of the poses inside the timed region)
 
---impl reference times the CPU oracle (the reference cannot be compiled here: no Eigen/OpenCV C++)
-on all host cores, one sequence per thread.
+--impl reference times the reference's own CPU implementation (oracle/_ref: its hot-path sources compiled
+against stand-in Eigen/OpenCV headers; the oracle port if that library is absent) on all host cores, one
+sequence per thread.
 """
 from __future__ import annotations
 
@@ -32,6 +33,11 @@ sys.path.insert(0, ROOT)
 
 W, H, LEVELS = 1241, 376, 4
 METRIC = "KITTI-shape tracking frames/s (pyramid + disparity/depth + LM align per frame)"
+CPU_KIND_NOTE = {
+    "reference": "the reference's own classes (oracle/_ref: its hot-path sources compiled unmodified against stand-in "
+                 "Eigen/OpenCV/Sophus headers, the loop of run_odometry_kitti_offline.cpp:95-271 around them)",
+    "port": "oracle port of the reference (oracle/_ref not present)",
+}
 
 
 def parse():
@@ -118,11 +124,29 @@ def render_sequences(seq_ids, n_frames, device):
     return out
 
 
-def cpu_tracking_fps(frames_u8, n_seq, n_frames, threads):
-    """Oracle tracker (CPU restatement of the reference loop): n_seq sequences over `threads` host
-    threads; frame 0 (keyframe init) is untimed like the GPU arm's. Returns (frames/s, timed frames)."""
+def cpu_tracker_factory():
+    """(kind, make_tracker): the reference's own classes (oracle/_ref: its first-party sources compiled against
+    stand-in Eigen/OpenCV headers) when that library exists, else the oracle port.  Both in the reference's own
+    arithmetic (fp32 sequential sums)."""
     import oracle
-    trackers = [oracle.Tracker(W, H, LEVELS) for _ in range(n_seq)]
+    from oracle import ref
+    lp = lambda: oracle.lm_params(sum_mode=oracle.SUM_FLOAT_SEQ)
+    dp = lambda: oracle.depth_params(sum_mode=oracle.SUM_FLOAT_SEQ)
+    if ref.available():
+        try:
+            ref.lib()
+            return "reference", lambda: ref.Tracker(W, H, LEVELS, lp(), dp())
+        except OSError:
+            pass
+    oracle.lib()
+    return "port", lambda: oracle.Tracker(W, H, LEVELS, lp(), dp())
+
+
+def cpu_tracking_fps(frames_u8, n_seq, n_frames, threads):
+    """CPU tracking loop (cpu_tracker_factory): n_seq sequences over `threads` host threads; frame 0
+    (keyframe init) is untimed like the GPU arm's. Returns (frames/s, timed frames, kind)."""
+    kind, make = cpu_tracker_factory()
+    trackers = [make() for _ in range(n_seq)]
     fl = frames_u8.astype(np.float32)
     for s, t in enumerate(trackers):
         t.step(fl[0, s, 0], fl[0, s, 1])
@@ -144,7 +168,7 @@ def cpu_tracking_fps(frames_u8, n_seq, n_frames, threads):
     dt = time.perf_counter() - t0
     for t in trackers:
         t.close()
-    return n_seq * (n_frames - 1) / dt, n_seq * (n_frames - 1)
+    return n_seq * (n_frames - 1) / dt, n_seq * (n_frames - 1), kind
 
 
 def run_reference(args, rank, world):
@@ -157,10 +181,9 @@ def run_reference(args, rank, world):
     n_frames = 1 + args.warmup + args.steps
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     frames = render_sequences(list(range(n_seq)), n_frames, dev).cpu().numpy()
-    import oracle
-    oracle.lib()
+    kind, make = cpu_tracker_factory()
     # warm-up steps are part of the same trajectory: time only the last `steps` frames
-    trackers = [oracle.Tracker(W, H, LEVELS) for _ in range(n_seq)]
+    trackers = [make() for _ in range(n_seq)]
     fl = frames.astype(np.float32)
 
     def advance(s, f0, f1):
@@ -184,8 +207,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, {"sequences_per_step": n_seq}),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_seq, "kind": "port",
-                         "sample": f"{n_seq} sequences x {args.steps} frames, one oracle tracker per host thread"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_seq, "kind": kind,
+                         "sample": f"{n_seq} sequences x {args.steps} frames, one tracker per host thread; " + CPU_KIND_NOTE[kind]},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -398,10 +421,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_seqs, S)
         nf = min(n_frames, 1 + 30)
-        fps, nfr = cpu_tracking_fps(frames_u8[:nf, :ns].cpu().numpy(), ns, nf, threads=1)
-        cpu = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-               "sample": f"{ns} sequences x {nf - 1} frames of the same workload, oracle tracker, 1 thread "
-                         f"(host has {os.cpu_count()} logical cores)"}
+        fps, nfr, kind = cpu_tracking_fps(frames_u8[:nf, :ns].cpu().numpy(), ns, nf, threads=1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
+               "sample": f"{ns} sequences x {nf - 1} frames of the same workload, 1 thread "
+                         f"(host has {os.cpu_count()} logical cores); " + CPU_KIND_NOTE[kind]}
 
     if rank == 0:
         line = {

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "group_sync.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kSelMax = 80;       // "if (valid_count >= 80) break", src/depth_estimate.cpp:333-339
@@ -135,6 +137,83 @@ __global__ void __launch_bounds__(kSelThreads) k_select(int W, int H, odo_depth_
   }
 }
 
+// Register-resident variant for blocks of at most 32 * NPL pixels (KITTI: 38 x 23 = 874 <= 896): ONE WARP per
+// block of the selection grid.  Lane `l` holds the magnitudes of block pixels l, l + 32, ... as bit patterns;
+// the k-th smallest is built bit by bit (largest T with #{v < T} <= k: 31 rounds of NPL compares and one
+// REDUX.ADD), and the ordered first-80 scan is a ballot/popc per 32-pixel slice -- no shared memory, no
+// barrier, no atomics; about a quarter of the instructions of k_select.  Same results bit for bit.
+constexpr int kSelWarpsPerCta = 4;
+
+template <int NPL>
+__global__ void __launch_bounds__(32 * kSelWarpsPerCta) k_select_warp(int W, int H, odo_depth_params p, DepthWork d) {
+  const int lane = threadIdx.x & 31;
+  const int block_id = blockIdx.x * kSelWarpsPerCta + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (block_id >= kGridBlocks) return;
+  const int64_t npx = (int64_t)W * H;
+  const float* bl = d.blurL + b * d.blurL_stride;
+  uint8_t* val = d.val + b * npx;
+  const int bw = (W - p.boundary * 2) / 32, bh = (H - p.boundary * 2) / 16;
+  const int start_y = p.boundary + (block_id / 32) * bh;
+  const int start_x = p.boundary + (block_id % 32) * bw;
+  const int n = bw * bh;
+  const int dx = 32 % bw, dy = 32 / bw;  // pixel i + 32 from pixel i inside the block
+  unsigned v[NPL];
+  {
+    int x = lane % bw, y = lane / bw;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) {
+      // 0xffffffff (a NaN pattern): never below a candidate threshold, never above the block threshold
+      v[j] = (j * 32 + lane < n) ? __float_as_uint(grad_mag(bl, W, start_y + y, start_x + x)) : 0xffffffffu;
+      x += dx;
+      y += dy;
+      if (x >= bw) { x -= bw; y++; }
+    }
+  }
+  // block_grad[n / 2] after std::nth_element (:324): magnitudes are >= +0, so bit patterns order like values
+  const int k = n / 2;
+  unsigned ans = 0u;
+#pragma unroll 1
+  for (int bit = 30; bit >= 0; bit--) {
+    const unsigned cand = ans | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) cnt += (v[j] < cand) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt <= k) ans = cand;
+  }
+  const float block_th = __fadd_rn(__uint_as_float(ans), p.grad_th);  // :325
+  // first <= 80 pixels with mag > th in raster order, :327-341
+  int* sel = d.sel_xy + ((int64_t)b * kGridBlocks + block_id) * kSelMax;
+  int run = 0;
+  {
+    int x = lane % bw, y = lane / bw;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) {
+      if (run < kSelMax) {  // warp uniform
+        const bool f = __uint_as_float(v[j]) > block_th;
+        const unsigned mk = __ballot_sync(0xffffffffu, f);
+        const int rank = run + __popc(mk & ((1u << lane) - 1u));
+        if (f && rank < kSelMax) {
+          val[(int64_t)(start_y + y) * W + start_x + x] = 1;
+          sel[rank] = ((start_y + y) << 16) | (start_x + x);
+        }
+        run += __popc(mk);
+      }
+      x += dx;
+      y += dy;
+      if (x >= bw) { x -= bw; y++; }
+    }
+  }
+  const int cnt = min(run, kSelMax);
+  for (int t = lane; t < kSelMax; t += 32)
+    if (t >= cnt) sel[t] = -1;  // unfilled slots of this block's list
+  if (lane == 0) {
+    d.sel_count[b * kGridBlocks + block_id] = cnt;
+    atomicAdd(&d.stats[b].n_selected, cnt);
+  }
+}
+
 // ---- disparity line search ----------------------------------------------------------------------------
 // Work item = one image row of one sequence.  The CTA compacts the row of the validity mask into an
 // ascending list of selected columns, stages the five right rows y-2..y+2 it needs in shared memory
@@ -163,7 +242,11 @@ constexpr int kDispThreads = 128;
 constexpr int kDispWarps = kDispThreads / 32;
 constexpr int kDispP = 4;
 
-__host__ __device__ inline int q_pitch(int W) { return (W + 7) & ~7; }  // q / Er planes: 16-byte aligned rows
+// Row pitch of the q planes = the shared-memory pitch the line search is instantiated with (a compile-time
+// constant there: every tap of a left pattern is then a load at an immediate offset from one base address).
+__host__ __device__ inline int q_pitch(int W) {
+  return (W + 12 <= 1280) ? 1280 : (W + 12 <= 2048) ? 2048 : (W + 12 <= 4096) ? 4096 : ((W + 7) & ~7);
+}
 
 __global__ void __launch_bounds__(256) k_quantize(int W, int H, DepthWork d) {
   const int b = blockIdx.z;
@@ -210,7 +293,7 @@ template <> struct DispTraits<false> {
 // rows[r * PITCH + c + 2] so that the taps at c - 2 of the first candidate stay inside the row.
 template <bool QPATH, int PITCH>
 __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W, int H, odo_depth_params p, DepthWork d,
-                                                                          int q_eligible) {
+                                                                          int q_eligible, int pack_ok) {
   typedef typename DispTraits<QPATH>::elem elem_t;
   extern __shared__ __align__(16) unsigned char s_raw[];
   elem_t* s_rows = reinterpret_cast<elem_t*>(s_raw);                       // [5][PITCH]
@@ -250,7 +333,7 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
   // ---- stage right rows y-2 .. y+2, columns [0, xlast + 3) (candidates end at xlast - 1, taps reach +2) ----
   const int ncol = min(xlast + 3, W);
   if (QPATH) {
-    const int QP = q_pitch(W);
+    constexpr int QP = PITCH;  // == q_pitch(W)
     const int64_t qpx = (int64_t)QP * H;
     const uint16_t* src = d.qR + b * qpx + (int64_t)(y - 2) * QP;
     const int nv = (ncol + 7) >> 3;  // 8 u16 per 16-byte load; plane rows are padded to a multiple of 8
@@ -298,7 +381,7 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
     int rx = bnd + lane;
 
     if (QPATH) {
-      const int QP = q_pitch(W);
+      constexpr int QP = PITCH;  // == q_pitch(W)
       const uint16_t* lq = d.qL + b * (int64_t)QP * H + (int64_t)y * QP;
       int l2[kDispP][8], El[kDispP], best[kDispP];
 #pragma unroll
@@ -347,31 +430,52 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
           }
         }
       }
+      // Warp argmin.  256 * SSD = El - best is exact; the winner only matters while it can pass ssd_th, so the
+      // cost is clamped to kCap (> 256 * ssd_th, checked by the host: pack_ok) and packed above the column into
+      // one 31-bit key: a single REDUX.MIN per pixel then yields the smallest cost and, among equal costs, the
+      // smallest column -- the reference's first minimum (:382-386).  A clamped winner is rejected below
+      // whatever its column.  pack_ok == 0 (huge ssd_th): shuffle argmin on the unclamped values.
+      constexpr int kKeyBits = (PITCH <= 2048) ? 11 : 12;
+      constexpr int kCap = (1 << (31 - kKeyBits)) - 1;
+      int w_ssd = 0, w_rx = -1, w_x = 0;
 #pragma unroll
       for (int i = 0; i < kDispP; i++) {
         int ssd = El[i] - best[i];  // 256 * SSD, exact
+        int wrx = brx[i];
+        if (pack_ok) {
+          const unsigned key = (brx[i] < 0) ? 0x7fffffffu : (((unsigned)min(ssd, kCap) << kKeyBits) | (unsigned)brx[i]);
+          const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+          ssd = (int)(kmin >> kKeyBits);
+          wrx = (kmin == 0x7fffffffu) ? -1 : (int)(kmin & ((1u << kKeyBits) - 1u));
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const int ob = __shfl_xor_sync(0xffffffffu, ssd, o);
-          const int orx = __shfl_xor_sync(0xffffffffu, brx[i], o);
-          const bool take = (orx >= 0) && (brx[i] < 0 || ob < ssd || (ob == ssd && orx < brx[i]));
-          if (take) {
-            ssd = ob;
-            brx[i] = orx;
+          for (int o = 16; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, ssd, o);
+            const int orx = __shfl_xor_sync(0xffffffffu, wrx, o);
+            const bool take = (orx >= 0) && (wrx < 0 || ob < ssd || (ob == ssd && orx < wrx));
+            if (take) {
+              ssd = ob;
+              wrx = orx;
+            }
           }
         }
-        if (lane == i && g * kDispP + i < n && brx[i] >= 0) {  // absent pixels of a short group took part in phase A
-          const int x = xs[i];
-          const int64_t o = b * npx + (int64_t)y * W + x;
-          // exact in fp32 below 2^24; anything larger is far above ssd_th (< 2^16) whatever its rounding
-          const float fssd = __fmul_rn((float)ssd, 1.0f / 256.0f);
-          if (!(fssd > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
-            const float disp = (float)abs(x - brx[i]);
-            if (d.disp) d.disp[o] = disp;
-            d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
-            if (d.match_x) d.match_x[o] = brx[i];
-            atomicAdd(&d.stats[b].n_matched, 1);
-          }
+        if (lane == i) {  // lane i keeps pixel i's result; the four write-backs below run as one pass
+          w_ssd = ssd;
+          w_rx = (g * kDispP + i < n) ? wrx : -1;  // absent pixels of a short group took part in phase A
+          w_x = xs[i];
+        }
+      }
+      if (w_rx >= 0) {
+        const int x = w_x;
+        const int64_t o = b * npx + (int64_t)y * W + x;
+        // exact in fp32 below 2^24; anything larger is far above ssd_th (< 2^16) whatever its rounding
+        const float fssd = __fmul_rn((float)w_ssd, 1.0f / 256.0f);
+        if (!(fssd > p.ssd_th)) {  // "if (smallest_ssd > ssd_th_) continue", :388
+          const float disp = (float)abs(x - w_rx);
+          if (d.disp) d.disp[o] = disp;
+          d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
+          if (d.match_x) d.match_x[o] = w_rx;
+          atomicAdd(&d.stats[b].n_matched, 1);
         }
       }
     } else {
@@ -817,7 +921,11 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
   cudaMemsetAsync(d.stats, 0, sizeof(odo_depth_stats) * batch, c->stream);
   if (d.match_x) cudaMemsetAsync(d.match_x, 0xff, npx * batch * 4, c->stream);
   if (d.min_ssd) cudaMemsetAsync(d.min_ssd, 0, npx * batch * 4, c->stream);
-  k_select<<<dim3(kGridBlocks, batch), kSelThreads, 0, c->stream>>>(w, h, p, d);
+  const int bn = ((w - 2 * p.boundary) / 32) * ((h - 2 * p.boundary) / 16);
+  if (bn <= 32 * 28 && !std::getenv("ODO_SELECT_CTA"))
+    k_select_warp<28><<<dim3(kGridBlocks / kSelWarpsPerCta, batch), 32 * kSelWarpsPerCta, 0, c->stream>>>(w, h, p, d);
+  else
+    k_select<<<dim3(kGridBlocks, batch), kSelThreads, 0, c->stream>>>(w, h, p, d);
   c->launches++;
 }
 
@@ -831,7 +939,11 @@ static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params&
     cudaFuncSetAttribute(k_disparity<QPATH, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_disparity<QPATH, PITCH><<<dim3(h - 2 * p.boundary, batch), kDispThreads, smem, c->stream>>>(w, h, p, d, q_eligible);
+  // one-instruction warp argmin on packed (cost, column) keys: needs 256 * ssd_th below the clamp (see kernel)
+  const int key_bits = (PITCH <= 2048) ? 11 : 12;
+  const int pack_ok = (QPATH && p.ssd_th * 256.0f < (float)((1 << (31 - key_bits)) - 1)) ? 1 : 0;
+  k_disparity<QPATH, PITCH><<<dim3(h - 2 * p.boundary, batch), kDispThreads, smem, c->stream>>>(w, h, p, d, q_eligible,
+                                                                                               pack_ok);
   c->launches++;
 }
 

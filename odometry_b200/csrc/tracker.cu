@@ -365,6 +365,10 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   const int gmax = (int)((t->npx + 16383) / 16384);
   if (G > gmax) G = gmax;
   if (G < 1) G = 1;
+  if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // experiment knob
+    const int g = std::atoi(e);
+    if (g >= 1 && g <= gmax && g * n_seq <= lm_max_ctas(c)) G = g;
+  }
   t->G_lm = G;
   size_t bytes = 0;
   const size_t in_b = al256(sizeof(float) * t->npx * n_seq);
@@ -421,10 +425,6 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming);
   for (int k = 0; k < 2; k++)
     for (int i = 0; i < 2; i++) cudaEventCreate(&t->ev_lm[k][i]);
-  if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // experiment knob
-    const int g = std::atoi(e);
-    if (g >= 1 && g <= t->G_lm) t->G_lm = g;
-  }
   for (int k = 0; k < 2; k++) {
     for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[k][i]);
     cudaEventCreateWithFlags(&t->ev_copied[k], cudaEventDisableTiming);

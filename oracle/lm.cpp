@@ -154,20 +154,26 @@ float compute_weights(Residuals& R, int robust, float delta, int sum_mode) {
 }
 
 // jtw = J^T W ; jtwj = jtw J ; jtw r ; r^T W r   (src/lm_optimizer.cpp:129,145-149)
-void normal_sums(const Residuals& R, int sum_mode, double H[21], double g[6], double* E) {
+// Hlow (optional, FLOAT_SEQ only): the 15 entries BELOW the diagonal, row-major (10 20 21 30 ..).  jtwj(a,b) =
+// sum (J_a w) J_b rounds differently from jtwj(b,a) = sum (J_b w) J_a, so the reference's fp32 matrix is
+// not exactly symmetric and its QR sees both halves (checked against oracle/_ref).
+void normal_sums(const Residuals& R, int sum_mode, double H[21], double g[6], double* E, float* Hlow = nullptr) {
   if (sum_mode == ORC_SUM_FLOAT_SEQ) {
-    float Hf[21] = {0}, gf[6] = {0}, Ef = 0.f;
+    float Hf[21] = {0}, gf[6] = {0}, Ef = 0.f, Hl[15] = {0};
     for (int i = 0; i < R.n; i++) {
       const float* J = &R.J[(size_t)i * 6];
       const float w = R.w[i], r = R.r[i];
-      int k = 0;
+      int k = 0, kl = 0;
       for (int a = 0; a < 6; a++) {
         const float jw = J[a] * w;
+        for (int b = 0; b < a; b++) Hl[kl++] += jw * J[b];
         for (int b = a; b < 6; b++) Hf[k++] += jw * J[b];
         gf[a] += jw * r;
       }
       Ef += (r * w) * r;
     }
+    if (Hlow)
+      for (int k = 0; k < 15; k++) Hlow[k] = Hl[k];
     for (int k = 0; k < 21; k++) H[k] = Hf[k];
     for (int k = 0; k < 6; k++) g[k] = gf[k];
     *E = Ef;
@@ -245,10 +251,16 @@ int orc_lm_solve(const float* pyr1, const float* dep1, const float* pyr2, int w,
       if (R.n == 0) { status = -1; break; }
       compute_weights(R, p->robust, p->huber_delta, p->sum_mode);
       double H[21], g[6], E;
-      normal_sums(R, p->sum_mode, H, g, &E);
+      float Hlow[15];
+      normal_sums(R, p->sum_mode, H, g, &E, Hlow);
       if (p->sum_mode == ORC_SUM_FLOAT_SEQ) {
-        // (1/N) * r^T * W * r, fp32
-        err_now = (1.0f / (float)R.n) * (float)E;
+        // "(float(1.0) / float(N)) * residuals.transpose() * weights * residuals" (:129) associates as
+        // ((s * r^T) * W) * r: each term is ((s * r_i) * w_i) * r_i, summed in fp32 (checked against the
+        // reference's own code, oracle/_ref)
+        const float s = 1.0f / (float)R.n;
+        float acc = ((s * R.r[0]) * R.w[0]) * R.r[0];
+        for (int i = 1; i < R.n; i++) acc = acc + ((s * R.r[i]) * R.w[i]) * R.r[i];
+        err_now = acc;
       } else {
         err_now = (float)(E / (double)R.n);
       }
@@ -273,6 +285,11 @@ int orc_lm_solve(const float* pyr1, const float* dep1, const float* pyr2, int w,
       int k = 0;
       for (int a = 0; a < 6; a++)
         for (int c = a; c < 6; c++) { Hf[a][c] = (float)H[k]; Hf[c][a] = (float)H[k]; k++; }
+      if (p->sum_mode == ORC_SUM_FLOAT_SEQ) {  // the reference's lower triangle (see normal_sums)
+        int kl = 0;
+        for (int a = 0; a < 6; a++)
+          for (int c = 0; c < a; c++) Hf[a][c] = Hlow[kl++];
+      }
       for (int c = 0; c < 6; c++)
         for (int r = 0; r < 6; r++) A[c * 6 + r] = Hf[r][c] + lambda * (r == c ? Hf[r][c] : 0.0f);
       for (int a = 0; a < 6; a++) b[a] = -(float)g[a];
