@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-seqs", type=int, default=2, help="sequences of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="kitti", choices=["kitti", "4k"],
+                    help="kitti: the headline tracking step (BASELINE.json configs 3/4); 4k: config 5, 3840x2160 "
+                         "6-level pyramid + all-pixel dense LM alignment of each new frame against a keyframe")
     return ap.parse_args()
 
 
@@ -215,13 +218,248 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# config 5: 3840x2160, 6 levels, dense alignment (the HBM-bound stress case; no ComputeDepth: the reference
+# locks it to 376x1241, src/depth_estimate.cpp:46)
+# ---------------------------------------------------------------------------------------------------------
+W4, H4, LEVELS4 = 3840, 2160, 6
+METRIC_4K = "4K dense alignment frames/s (6-level image pyramid + all-pixel LM Solve per frame)"
+
+
+def render_4k(seq_id, n_frames, device):
+    """Keyframe (u8 image, exact inverse depth) and n_frames following frames (u8) of one 4K sequence; the
+    camera advances 0.02 m per frame (a 100 Hz camera at KITTI speed) so that every frame aligns against the
+    same keyframe.  Intrinsics are the reference's hard-coded KITTI constants (include/image_processing_global.h:
+    35-36): they are compiled into its hot path, so a 4K input means this wide-angle camera for it too."""
+    import torch
+    from odometry_b200 import synth
+    kw = dict(w=W4, h=H4, device=device, fx=synth.FX, cx=synth.CX, cy=synth.CY)
+    sc = synth.make_scene(1000 + seq_id, 2)
+    key, z = synth.render(sc, synth.pose_from_motion(), **kw)
+    inv = (1.0 / z).to(torch.float32)
+    frames = torch.empty((n_frames, H4, W4), dtype=torch.uint8, device=device)
+    for f in range(n_frames):
+        t = f + 1
+        T = synth.pose_from_motion(0.0, 0.0, 0.02 * t, 0.0, math.radians(0.01 * t), 0.0)
+        frames[f], _ = synth.render(sc, T, **kw)
+    return key, inv, frames, (synth.FX, synth.CX, synth.CY)
+
+
+def lm_params_4k(mod, K):
+    """LM parameters of config 5 for `mod` (odometry_b200.capi or oracle): iters {10,20,30,30,30,30}, Huber 28."""
+    if hasattr(mod, "default_lm_params"):
+        p = mod.default_lm_params()
+    else:
+        p = mod.lm_params(sum_mode=mod.SUM_FLOAT_SEQ)
+    for l, it in enumerate((10, 20, 30, 30, 30, 30)):
+        p.max_iters[l] = it
+    p.K.fx, p.K.cx, p.K.cy = K
+    return p
+
+
+def config_4k(args):
+    return {"workload": "config 5: 3840x2160, 6-level image pyramid of every new frame + all-pixel dense LM alignment "
+                        "against a keyframe with exact dense inverse depth (one sequence per GPU)",
+            "frame": f"{W4}x{H4}", "levels": LEVELS4, "lm": "lambda 0.01, precision 0.995, iters {10,20,30,30,30,30}, Huber 28",
+            "trajectory": "0.02 m/frame forward, yaw 0.01 deg/frame; every frame aligns against frame 0; warm start from the previous pose",
+            "parallelism": f"one independent sequence per GPU x{args.gpus} GPUs, no collective",
+            "l2": "one linearisation at level 0 streams 396 MB of point list (> 126 MB L2); no explicit flush"}
+
+
+def run_reference_4k(args, rank):
+    """--impl reference --workload 4k: the reference's Solve on 4K frames, one sequence per host thread."""
+    if rank != 0:
+        return
+    import torch
+    import oracle
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    n_seq = max(1, min(cores, 8))      # ~1.3 GB of Jacobian / weights per solve
+    K_steps = max(1, min(args.steps, 1))
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    use_ref = ref.available()
+    data = []
+    for s in range(n_seq):
+        key, inv, frames, K = render_4k(s, 1, dev)
+        data.append((key.cpu().numpy().astype(np.float32), inv.cpu().numpy(), frames[0].cpu().numpy().astype(np.float32)))
+    p = lm_params_4k(oracle, K)
+    out = [None] * n_seq
+
+    def work(s):
+        k, d, f = data[s]
+        if use_ref:
+            out[s] = ref.lm_solve(k, d, f, LEVELS4, p)
+        else:
+            o1, od, o2 = (oracle.image_pyramid(k, LEVELS4, True, packed=True), oracle.depth_pyramid(d, LEVELS4, False, packed=True),
+                          oracle.image_pyramid(f, LEVELS4, True, packed=True))
+            out[s] = oracle.lm_solve(o1, od, o2, W4, H4, LEVELS4, p)[:2]
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(s,)) for s in range(n_seq)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    fps = n_seq * K_steps / dt
+    kind = "reference" if use_ref else "port"
+    line = {"impl": "reference", "metric": METRIC_4K, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": K_steps, "warmup": 0, "ms_per_step": dt / K_steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_4k(args),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_seq, "kind": kind,
+                             "sample": f"{n_seq} sequences x 1 frame (keyframe pyramids + frame pyramid + Solve), one per host thread; "
+                                       + CPU_KIND_NOTE[kind]},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_4k(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from odometry_b200 import capi, shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    key8, inv, frames8, Kcam = render_4k(rank, Wm + K, dev)
+    stream = torch.cuda.current_stream(dev)
+    ctx = capi.Context(local_rank, stream.cuda_stream)   # the context runs on torch's stream: events below see its work
+    p = lm_params_4k(capi, Kcam)
+    key_f = key8.to(torch.float32)
+    p1 = ctx.image_pyramid_dev(key_f.data_ptr(), W4, H4, LEVELS4, True)
+    d1 = ctx.depth_pyramid_dev(inv.data_ptr(), W4, H4, LEVELS4, False)
+    ctx.sync()
+    frames_f = frames8.to(torch.float32)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc = {"pyr": 0.0, "lm": 0.0, "iters": np.zeros(LEVELS4, np.int64), "ok": True}
+
+    def step_dev(f, T_prev, timed_stages):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(stream)
+        p2 = ctx.image_pyramid_dev(frames_f[f].data_ptr(), W4, H4, LEVELS4, True)
+        e1.record(stream)
+        rc, T, st = ctx.lm_solve(p1, d1, p2, p, T_prev)
+        e2.record(stream)
+        p2.release()
+        if timed_stages:
+            e2.synchronize()
+            acc["pyr"] += e0.elapsed_time(e1)
+            acc["lm"] += e1.elapsed_time(e2)
+            acc["iters"] += np.array(list(st.iters)[:LEVELS4])
+            acc["ok"] &= (rc == 0)
+        return T
+
+    def run(f0, f1, T, stepfn, timed_stages=False):
+        for f in range(f0, f1):
+            T = stepfn(f, T, timed_stages)
+        return T
+
+    def timed(fn):
+        shard.barrier(dev)
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        r = fn()
+        e1.record(stream)
+        shard.barrier(dev)
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev), r
+
+    T0 = np.eye(4, dtype=np.float32)
+    T = run(0, Wm, T0, step_dev)
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    sampler.start()
+    ms_total, T_last = timed(lambda: run(Wm, Wm + K, T, step_dev, True))
+    clocks = sampler.result()
+    launches = ctx.launch_count() - launches0
+    value = world * K / (ms_total * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        host = frames_f.cpu().pin_memory()
+
+        def step_host(f, T_prev, _):
+            p2 = ctx.image_pyramid(host[f].numpy(), LEVELS4, True)      # H2D of the 33 MB frame inside the call
+            rc, Tn, st = ctx.lm_solve(p1, d1, p2, p, T_prev)           # D2H of the result inside the call
+            p2.release()
+            return Tn
+
+        Tw = run(0, Wm, T0, step_host)
+        ms_e2e, _ = timed(lambda: run(Wm, Wm + K, Tw, step_host))
+        e2e = {"value": world * K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": W4 * H4 * 4 + 64,
+               "d2h_bytes_per_step": 1680, "ms_per_step": ms_e2e / K,
+               "host_buffers": "pinned float32 (CV_32F) frame", "api": "odo_image_pyramid_build + odo_lm_solve"}
+        del host
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    lvl_px = [(W4 >> l) * (H4 >> l) for l in range(LEVELS4)]
+    iters = acc["iters"] / K
+    lm_bytes = float(sum(12 * lvl_px[l] * iters[l] for l in range(LEVELS4)))   # SURVEY 8(d): 12 B per pixel per linearisation
+    pyr_bytes = 4 * (lvl_px[0] + sum(lvl_px))
+    lm_ms, pyr_ms = acc["lm"] / K, acc["pyr"] / K
+    ach = lm_bytes / (lm_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_lm_solve", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "launch_ms": lm_ms, "algorithmic_bytes_per_launch": lm_bytes,
+            "linearisations_per_level": [float(x) for x in iters],
+            "list_bytes_per_launch": float(sum((48 + 8) * max(((W4 >> l) - 8) * ((H4 >> l) - 8), 0) * iters[l] for l in range(LEVELS4))),
+            "stage_ms_per_step": {"image_pyramid": pyr_ms, "lm_solve": lm_ms},
+            "per_stage_gbs": {"image_pyramid": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "lm_solve": ach}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        from oracle import ref
+        po = lm_params_4k(oracle, Kcam)
+        k_np, d_np, f_np = key_f.cpu().numpy(), inv.cpu().numpy(), frames_f[Wm].cpu().numpy()
+        t0 = time.perf_counter()
+        if ref.available():
+            ref.lm_solve(k_np, d_np, f_np, LEVELS4, po)
+            kind = "reference"
+        else:
+            oracle.lm_solve(oracle.image_pyramid(k_np, LEVELS4, True, packed=True), oracle.depth_pyramid(d_np, LEVELS4, False, packed=True),
+                            oracle.image_pyramid(f_np, LEVELS4, True, packed=True), W4, H4, LEVELS4, po)
+            kind = "port"
+        dt = time.perf_counter() - t0
+        cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+               "sample": "1 frame (3 pyramid builds + one cold-started Solve), 1 thread; " + CPU_KIND_NOTE[kind]}
+
+    if rank == 0:
+        line = {"metric": METRIC_4K, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_4k(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "frames_per_step": world, "all_status_ok": bool(acc["ok"]),
+                "final_pose_translation": [float(x) for x in T_last[:3, 3]]}
+        print(json.dumps(line), flush=True)
+    p1.release()
+    d1.release()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "4k":
+            run_reference_4k(args, rank)
+        else:
+            run_reference(args, rank, world)
+        return
+    if args.workload == "4k":
+        run_4k(args, rank, local_rank, world)
         return
 
     import torch

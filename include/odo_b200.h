@@ -96,6 +96,12 @@ void odo_default_depth_params(odo_depth_params* p);  /* run_odometry_kitti_offli
  * (include/image_pyramid.h:51, src/image_pyramid.cpp:30-37). */
 int  odo_image_pyramid_build(odo_ctx* ctx, const float* img, int w, int h, int levels, int smooth, odo_pyr** out);
 int  odo_depth_pyramid_build(odo_ctx* ctx, const float* dep, int w, int h, int levels, int smooth, odo_pyr** out);
+/* Same builders for an image that is already resident on the device (w*h float32, tightly packed): no copy,
+ * the kernels read the caller's buffer in place, and the call returns without waiting -- the work is ordered on
+ * the context's stream ahead of any later call on this context.  The buffer must stay untouched until a later
+ * synchronising call (odo_ctx_sync, odo_lm_solve, odo_pyr_download) has returned. */
+int  odo_image_pyramid_build_dev(odo_ctx* ctx, const float* img_dev, int w, int h, int levels, int smooth, odo_pyr** out);
+int  odo_depth_pyramid_build_dev(odo_ctx* ctx, const float* dep_dev, int w, int h, int levels, int smooth, odo_pyr** out);
 /* GetNumberLevels / GetPyramidImage / GetPyramidDepth (include/image_pyramid.h:33,36,60,63) */
 int  odo_pyr_levels(const odo_pyr* p);
 int  odo_pyr_level_size(const odo_pyr* p, int level, int* w, int* h);

@@ -48,6 +48,7 @@ EXPORTS = [
     "odo_version", "odo_ctx_create", "odo_ctx_destroy", "odo_ctx_sync", "odo_last_error",
     "odo_ctx_launch_count", "odo_default_intrinsics", "odo_default_lm_params",
     "odo_default_depth_params", "odo_image_pyramid_build", "odo_depth_pyramid_build",
+    "odo_image_pyramid_build_dev", "odo_depth_pyramid_build_dev",
     "odo_pyr_levels", "odo_pyr_level_size", "odo_pyr_download", "odo_pyr_release",
     "odo_compute_depth", "odo_select_pixels", "odo_disparity_search", "odo_depth_optimize",
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
@@ -194,6 +195,19 @@ class Context:
         hgt, wid = dep.shape
         out = C.c_void_p()
         if lib().odo_depth_pyramid_build(self.h, _p(dep), wid, hgt, levels, int(bool(smooth)), C.byref(out)) != 0:
+            raise OdoError(self.last_error())
+        return Pyramid(self, out)
+
+    def image_pyramid_dev(self, dev_ptr, wid, hgt, levels=4, smooth=True) -> Pyramid:
+        """Image already on the device (float32 [hgt][wid]); stream ordered, returns without waiting."""
+        out = C.c_void_p()
+        if lib().odo_image_pyramid_build_dev(self.h, C.c_void_p(dev_ptr), wid, hgt, levels, int(bool(smooth)), C.byref(out)) != 0:
+            raise OdoError(self.last_error())
+        return Pyramid(self, out)
+
+    def depth_pyramid_dev(self, dev_ptr, wid, hgt, levels=4, smooth=False) -> Pyramid:
+        out = C.c_void_p()
+        if lib().odo_depth_pyramid_build_dev(self.h, C.c_void_p(dev_ptr), wid, hgt, levels, int(bool(smooth)), C.byref(out)) != 0:
             raise OdoError(self.last_error())
         return Pyramid(self, out)
 

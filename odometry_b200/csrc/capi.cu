@@ -112,7 +112,8 @@ const char* odo_last_error(const odo_ctx* c) { return c ? c->err.c_str() : "null
 int64_t odo_ctx_launch_count(const odo_ctx* c) { return c ? c->launches : 0; }
 
 // ---- pyramids --------------------------------------------------------------------------------------
-static int pyr_build(odo_ctx* c, const float* host, int w, int h, int levels, int smooth, int kind, odo_pyr** out) {
+static int pyr_build(odo_ctx* c, const float* host, int w, int h, int levels, int smooth, int kind, odo_pyr** out,
+                     bool dev_input = false) {
   if (!c || !host || !out || w < 1 || h < 1 || levels < 1 || levels > ODO_MAX_LEVELS) return -1;
   *out = nullptr;
   ODO_CUDA_OK(c, cudaSetDevice(c->device));
@@ -122,8 +123,13 @@ static int pyr_build(odo_ctx* c, const float* host, int w, int h, int levels, in
     return -1;
   }
   const size_t n0 = (size_t)w * h;
-  float* in = (float*)ctx_scratch(c, SLOT_IN0, n0 * sizeof(float));
-  if (!in) return -1;
+  // device input: the kernels read the caller's buffer in place and the call returns without waiting (the
+  // work is ordered on the context's stream like every later call on this context)
+  const float* in = host;
+  if (!dev_input) {
+    in = (float*)ctx_scratch(c, SLOT_IN0, n0 * sizeof(float));
+    if (!in) return -1;
+  }
   odo_pyr* p = new odo_pyr();
   p->g = g;
   p->kind = kind;
@@ -140,11 +146,12 @@ static int pyr_build(odo_ctx* c, const float* host, int w, int h, int levels, in
     c->err = "cudaMalloc failed";
     return -1;
   }
-  cudaError_t e = cudaMemcpyAsync(in, host, n0 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  cudaError_t e = dev_input ? cudaSuccess
+                            : cudaMemcpyAsync((float*)in, host, n0 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
     if (kind == 0) launch_image_pyramid(c, in, 0, p->d, 0, g, smooth, 1);
     else launch_depth_pyramid(c, in, 0, p->d, 0, g, smooth, 1);
-    e = cudaStreamSynchronize(c->stream);
+    e = dev_input ? cudaGetLastError() : cudaStreamSynchronize(c->stream);
   }
   if (e != cudaSuccess) {
     c->err = std::string("pyramid build: ") + cudaGetErrorString(e);
@@ -162,6 +169,14 @@ int odo_image_pyramid_build(odo_ctx* c, const float* img, int w, int h, int leve
 
 int odo_depth_pyramid_build(odo_ctx* c, const float* dep, int w, int h, int levels, int smooth, odo_pyr** out) {
   return pyr_build(c, dep, w, h, levels, smooth, 1, out);
+}
+
+int odo_image_pyramid_build_dev(odo_ctx* c, const float* img_dev, int w, int h, int levels, int smooth, odo_pyr** out) {
+  return pyr_build(c, img_dev, w, h, levels, smooth, 0, out, true);
+}
+
+int odo_depth_pyramid_build_dev(odo_ctx* c, const float* dep_dev, int w, int h, int levels, int smooth, odo_pyr** out) {
+  return pyr_build(c, dep_dev, w, h, levels, smooth, 1, out, true);
 }
 
 int odo_pyr_levels(const odo_pyr* p) { return p ? p->g.levels : -1; }

@@ -8,12 +8,14 @@
  * (odometry_b200/, libodo_b200.so) never links, imports or calls anything in this directory.
  *
  * Parity pinning status (see DESIGN.md "Oracle"):
- *   - the reference holds NO golden vectors / KATs for this path and cannot be
- *     compiled here (no Eigen / OpenCV C++ headers).  The three OpenCV primitives it calls
- *     (GaussianBlur 3x3, pyrDown, medianBlur 3) are pinned against the in-container cv2 4.13.0
- *     (tests/golden/ + tests/test_oracle_cv2.py).  Everything above those primitives is a
- *     line-by-line restatement of the reference sources cited per function:
- *     "parity unpinned" by the reference's own tests, pinned only through cv2 for the primitives.
+ *   - the reference holds NO golden vectors / KATs for this path.  Its first-party
+ *     hot-path sources are compiled unmodified against stand-in Eigen/OpenCV/Sophus headers into
+ *     oracle/_ref/libodoref.so (oracle/Makefile, target _ref); in ORC_SUM_FLOAT_SEQ mode this
+ *     restatement is bit-identical to it (tests/test_oracle_ref.py).
+ *   - the three OpenCV primitives the reference calls (GaussianBlur 3x3, pyrDown, medianBlur 3) are
+ *     pinned against the in-container cv2 4.13.0 (tests/golden/, tests/test_oracle_primitives.py).
+ *   - unpinned: the bit-level behaviour of real Eigen (product contraction, QR) -- restated in
+ *     se3.cpp, within the north-star tolerances, not bit-checked.
  *
  * All matrices crossing this ABI that stand for Eigen::Matrix<float,4,4> are COLUMN-MAJOR float[16]
  * (include/data_types.h:24 of the reference: Affine4f = Eigen::Matrix<float,4,4>, default storage).
