@@ -141,6 +141,45 @@ int  odo_lm_linearize(odo_ctx* ctx, const odo_pyr* img1, const odo_pyr* dep1, co
                       int level, const float T[16], int robust, float huber_delta,
                       const odo_intrinsics* K, double H21[21], double g6[6], double* E, int* N, float* sigma);
 
+/* ---- undistort + rectify (camera front end) -------------------------------------------------------
+ * odo_camera replaces CameraPyramid (include/camera.h:15-118 of the reference, src/camera.cpp:12-83): the
+ * constructor's raw parameters, ConfigureCamera's per-level rectified intrinsics and remap tables, and
+ * UndistortRectify.  The arithmetic is OpenCV's (cv::initUndistortRectifyMap with 4 distortion coefficients,
+ * cv::remap INTER_LINEAR / BORDER_CONSTANT on CV_32FC1 maps), bit-exact for the rectified image.
+ * Matrices are row-major doubles as in cv::Mat_<double>: K_raw 3x3, R 3x3, P34 3x4. */
+typedef struct odo_camera odo_camera;
+#define ODO_PIX_U8  0   /* CV_8U  */
+#define ODO_PIX_F32 5   /* CV_32F */
+/* CameraPyramid::CameraPyramid, src/camera.cpp:12-38.  dist = k1 k2 r1 r2 (radial, radial, tangential, tangential) */
+int  odo_camera_create(int levels, const double K_raw[9], const double dist[4], double sensor_w, double sensor_h,
+                       int res_w, int res_h, odo_camera** out);
+void odo_camera_destroy(odo_camera* cam);
+/* ConfigureCamera, src/camera.cpp:40-70: intrinsic pyramid (f halves, c <- (c + .5) / 2 + .5) and the remap
+ * table for a new_w x new_h rectified image, computed on the device and kept resident there. */
+int  odo_camera_configure(odo_ctx* ctx, odo_camera* cam, const double R[9], const double P34[12], int new_w, int new_h);
+/* the same with caller-made tables (rmap_[0], rmap_[1] of include/camera.h:117); P34 optional */
+int  odo_camera_set_maps(odo_ctx* ctx, odo_camera* cam, const float* mapx, const float* mapy, int w, int h,
+                         const double P34[12]);
+/* accessors, include/camera.h:68-98: out5 = fx fy cx cy f_theta of `level` */
+int  odo_camera_levels(const odo_camera* cam);
+int  odo_camera_intrinsics(const odo_camera* cam, int level, double out5[5]);
+int  odo_camera_raw(const odo_camera* cam, double K_raw[9], double dist[4], double sensor_wh[2], int res_wh[2]);
+/* level-0 rectified fx, cx, cy as the floats the hot path takes in odo_lm_params.K / odo_depth_params.fx
+ * (replacing the KITTI constants hard-coded at include/image_processing_global.h:35-36,50-51) */
+int  odo_camera_lm_intrinsics(const odo_camera* cam, odo_intrinsics* K);
+int  odo_camera_map_size(const odo_camera* cam, int* w, int* h);
+int  odo_camera_maps_download(odo_ctx* ctx, const odo_camera* cam, float* mapx, float* mapy);
+/* UndistortRectify, src/camera.cpp:72-83 (INTER_LINEAR, BORDER_CONSTANT, Scalar(border_value)), without its
+ * 480x640 size lock (kept by the drop-in class).  src: sw x sh of src_type; dst: map-size image of dst_type.
+ * u8 -> u8 and f32 -> f32 are cv::remap; u8 -> f32 fuses the convertTo(CV_32F) that follows it
+ * (run_odometry_kitti_offline.cpp:348).  The _dev variant takes device buffers, `batch` images `*_stride`
+ * elements apart, runs on the context's stream and does not wait. */
+int  odo_camera_undistort_rectify(odo_ctx* ctx, const odo_camera* cam, const void* src, int src_type, int sw, int sh,
+                                  void* dst, int dst_type, double border_value);
+int  odo_camera_undistort_rectify_dev(odo_ctx* ctx, const odo_camera* cam, const void* src_dev, int src_type, int sw,
+                                      int sh, int64_t src_stride, void* dst_dev, int dst_type, int64_t dst_stride,
+                                      int batch, double border_value);
+
 /* ---- batched tracker -----------------------------------------------------------------------------
  * The per-frame loop of run_odometry_kitti_offline.cpp:95-271 (pyramid, Solve against the keyframe,
  * ComputeDepth, depth pyramid, keyframe rule, warm start) for n_seq independent stereo sequences
@@ -165,6 +204,13 @@ int  odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8
 int  odo_tracker_enqueue(odo_tracker* t, const float* const* left, const float* const* right);
 int  odo_tracker_enqueue_u8(odo_tracker* t, const uint8_t* const* left, const uint8_t* const* right);
 int  odo_tracker_collect(odo_tracker* t, float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
+/* Raw-camera ingest: after odo_tracker_set_rectify the tracker takes UNRECTIFIED u8 frames (raw_w x raw_h) and
+ * runs UndistortRectify (src/camera.cpp:72-83) + convertTo(CV_32F) on the device as the first kernel of the frame,
+ * so a frame costs raw_w * raw_h bytes per eye over PCIe.  The cameras' map size must equal the tracker's w x h. */
+int  odo_tracker_set_rectify(odo_tracker* t, const odo_camera* left, const odo_camera* right, int raw_w, int raw_h);
+int  odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, const uint8_t* const* right_raw);
+int  odo_tracker_step_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, const uint8_t* const* right_raw,
+                             float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 /* device-resident variant for the HBM-resident bench leg: images already on the device as one
  * contiguous [n_seq][h][w] float32 block per eye. */
 int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev,

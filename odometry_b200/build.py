@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libodo_b200.so")
-SOURCES = ["pyramid.cu", "lm.cu", "depth.cu", "tracker.cu", "capi.cu"]
+SOURCES = ["pyramid.cu", "lm.cu", "depth.cu", "tracker.cu", "capi.cu", "camera.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC", "-cudart", "static",

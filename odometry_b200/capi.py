@@ -54,7 +54,12 @@ EXPORTS = [
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
     "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev", "odo_tracker_stage_ms",
     "odo_tracker_enqueue", "odo_tracker_enqueue_u8", "odo_tracker_enqueue_dev", "odo_tracker_collect",
+    "odo_camera_create", "odo_camera_destroy", "odo_camera_configure", "odo_camera_set_maps", "odo_camera_levels",
+    "odo_camera_intrinsics", "odo_camera_raw", "odo_camera_lm_intrinsics", "odo_camera_map_size",
+    "odo_camera_maps_download", "odo_camera_undistort_rectify", "odo_camera_undistort_rectify_dev",
+    "odo_tracker_set_rectify", "odo_tracker_enqueue_raw_u8", "odo_tracker_step_raw_u8",
 ]
+PIX_U8, PIX_F32 = 0, 5
 STAGES = ["image_pyramid", "lm_solve", "blur_select", "disparity", "depth_refine", "depth_pyr_promote_prepare"]
 
 _lib = None
@@ -79,6 +84,22 @@ def lib():
         L.odo_pyr_release.argtypes = [C.c_void_p, C.c_void_p]
         L.odo_pyr_levels.argtypes = [C.c_void_p]
         L.odo_tracker_destroy.argtypes = [C.c_void_p]
+        dp = C.POINTER(C.c_double)
+        L.odo_camera_create.argtypes = [C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.odo_camera_destroy.argtypes = [C.c_void_p]
+        L.odo_camera_configure.argtypes = [C.c_void_p, C.c_void_p, dp, dp, C.c_int, C.c_int]
+        L.odo_camera_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, dp]
+        L.odo_camera_levels.argtypes = [C.c_void_p]
+        L.odo_camera_intrinsics.argtypes = [C.c_void_p, C.c_int, dp]
+        L.odo_camera_raw.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_int)]
+        L.odo_camera_lm_intrinsics.argtypes = [C.c_void_p, C.POINTER(Intrinsics)]
+        L.odo_camera_map_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.odo_camera_maps_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.odo_camera_undistort_rectify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_int, C.c_double]
+        L.odo_camera_undistort_rectify_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                       C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double]
+        L.odo_tracker_set_rectify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -272,6 +293,98 @@ class Context:
         return rc, val, disp, dep, st
 
 
+class Camera:
+    """CameraPyramid of the reference (include/camera.h:15-118) over odo_camera_*: raw parameters, ConfigureCamera
+    (per-level intrinsics + device-resident remap table) and UndistortRectify."""
+
+    def __init__(self, ctx: Context, levels, K_raw, dist, sensor=(0.0, 0.0), resolution=(0, 0)):
+        self.ctx = ctx
+        K = np.ascontiguousarray(K_raw, np.float64).reshape(9)
+        D = np.ascontiguousarray(dist, np.float64).reshape(4)
+        h = C.c_void_p()
+        rc = lib().odo_camera_create(levels, _p(K, C.c_double), _p(D, C.c_double), float(sensor[0]), float(sensor[1]),
+                                     int(resolution[0]), int(resolution[1]), C.byref(h))
+        if rc != 0:
+            raise OdoError("odo_camera_create failed")
+        self.h = h
+        ctx._children.add(self)
+
+    def configure(self, R, P34, new_size):
+        """ConfigureCamera(rectify_rotation, new_intrinsic34, new_size), src/camera.cpp:40-70; new_size = (w, h)."""
+        R = np.ascontiguousarray(R, np.float64).reshape(9)
+        P = np.ascontiguousarray(P34, np.float64).reshape(12)
+        rc = lib().odo_camera_configure(self.ctx.h, self.h, _p(R, C.c_double), _p(P, C.c_double), new_size[0], new_size[1])
+        if rc != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def set_maps(self, mapx, mapy, P34=None):
+        mapx, mapy = _f32(mapx), _f32(mapy)
+        hh, ww = mapx.shape
+        P = None if P34 is None else np.ascontiguousarray(P34, np.float64).reshape(12)
+        rc = lib().odo_camera_set_maps(self.ctx.h, self.h, mapx.ctypes.data, mapy.ctypes.data, ww, hh,
+                                       None if P is None else _p(P, C.c_double))
+        if rc != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def intrinsics(self, level):
+        out = np.zeros(5, np.float64)
+        if lib().odo_camera_intrinsics(self.h, level, _p(out, C.c_double)) != 0:
+            raise OdoError("camera not configured or level out of range")
+        return out
+
+    def lm_intrinsics(self) -> Intrinsics:
+        k = Intrinsics()
+        if lib().odo_camera_lm_intrinsics(self.h, C.byref(k)) != 0:
+            raise OdoError("camera not configured")
+        return k
+
+    def map_size(self):
+        w, h = C.c_int(), C.c_int()
+        if lib().odo_camera_map_size(self.h, C.byref(w), C.byref(h)) != 0:
+            raise OdoError("camera not configured")
+        return w.value, h.value
+
+    def maps(self):
+        w, h = self.map_size()
+        mx, my = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+        if lib().odo_camera_maps_download(self.ctx.h, self.h, mx.ctypes.data, my.ctypes.data) != 0:
+            raise OdoError(self.ctx.last_error())
+        return mx, my
+
+    def undistort_rectify(self, src, out_dtype=None, border_value=0.0):
+        """UndistortRectify(src_raw, dst, INTER_LINEAR, BORDER_CONSTANT, Scalar(border_value)), src/camera.cpp:72-83."""
+        src = np.ascontiguousarray(src)
+        if src.dtype not in (np.uint8, np.float32):
+            raise TypeError("u8 or float32 frames")
+        out_dtype = np.dtype(out_dtype or src.dtype)
+        w, h = self.map_size()
+        dst = np.empty((h, w), out_dtype)
+        code = {np.dtype(np.uint8): PIX_U8, np.dtype(np.float32): PIX_F32}
+        rc = lib().odo_camera_undistort_rectify(self.ctx.h, self.h, src.ctypes.data, code[src.dtype], src.shape[1],
+                                                src.shape[0], dst.ctypes.data, code[out_dtype], float(border_value))
+        if rc != 0:
+            raise OdoError(self.ctx.last_error())
+        return dst
+
+    def undistort_rectify_dev(self, src_ptr, src_u8, sw, sh, src_stride, dst_ptr, dst_u8, dst_stride, batch, border_value=0.0):
+        rc = lib().odo_camera_undistort_rectify_dev(self.ctx.h, self.h, C.c_void_p(src_ptr), PIX_U8 if src_u8 else PIX_F32,
+                                                    sw, sh, src_stride, C.c_void_p(dst_ptr), PIX_U8 if dst_u8 else PIX_F32,
+                                                    dst_stride, batch, float(border_value))
+        if rc != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def close(self):
+        if self.h:
+            lib().odo_camera_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Tracker:
     """Batched tracking loop (odo_tracker_*): n_seq sequences, one frame per sequence per step."""
 
@@ -314,6 +427,25 @@ class Tracker:
         fn = lib().odo_tracker_enqueue_u8 if u8 else lib().odo_tracker_enqueue
         if fn(self.h, la, ra) != 0:
             raise OdoError(self.ctx.last_error())
+
+    def set_rectify(self, cam_left: "Camera", cam_right: "Camera", raw_w, raw_h):
+        """Raw-camera ingest: later frames go through step_raw_u8 / enqueue_raw_ptrs as unrectified u8 images."""
+        self._cams = (cam_left, cam_right)
+        if lib().odo_tracker_set_rectify(self.h, cam_left.h, cam_right.h, raw_w, raw_h) != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def enqueue_raw_ptrs(self, left_ptrs, right_ptrs):
+        arr_t = C.c_void_p * self.n
+        if lib().odo_tracker_enqueue_raw_u8(self.h, arr_t(*left_ptrs), arr_t(*right_ptrs)) != 0:
+            raise OdoError(self.ctx.last_error())
+
+    def step_raw_u8(self, lefts, rights):
+        ls = [np.ascontiguousarray(a, dtype=np.uint8) for a in lefts]
+        rs = [np.ascontiguousarray(a, dtype=np.uint8) for a in rights]
+        arr_t = C.c_void_p * self.n
+        rc = lib().odo_tracker_step_raw_u8(self.h, arr_t(*[a.ctypes.data for a in ls]), arr_t(*[a.ctypes.data for a in rs]),
+                                           *self._outs())
+        return self._result(rc)
 
     def enqueue_dev(self, left_dev_ptr, right_dev_ptr):
         if lib().odo_tracker_enqueue_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr)) != 0:

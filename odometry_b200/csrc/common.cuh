@@ -190,3 +190,9 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch);
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch);
+
+// ---- camera.cu -----------------------------------------------------------------------------------
+// batched cv::remap (INTER_LINEAR, BORDER_CONSTANT) through a configured camera's table on the context's stream.
+// u8 sources may write the float image, the u8 image, or both.
+int launch_remap(odo_ctx* c, const odo_camera* cam, const void* src, int src_is_u8, int sw, int sh, int64_t sstride,
+                 float* dst_f, uint8_t* dst_8, int64_t dstride, int batch, double border);

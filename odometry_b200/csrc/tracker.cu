@@ -186,6 +186,10 @@ struct odo_tracker {
   // two ingest slots: the host->device copy of frame k+1 (copy stream) overlaps the kernels of frame k
   float *in_left[2] = {nullptr, nullptr}, *in_right[2] = {nullptr, nullptr};
   uint8_t* in_u8[2] = {nullptr, nullptr};
+  // raw-camera ingest (odo_tracker_set_rectify): unrectified u8 frames per slot, [2 eyes][n][raw_h * raw_w]
+  const odo_camera* cam[2] = {nullptr, nullptr};
+  int raw_w = 0, raw_h = 0;
+  uint8_t* in_raw[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   // the LM solve of a frame (latency bound: a chain of up to 90 dependent iterations that leaves most issue
   // slots idle) and its depth pipeline (throughput bound) are independent until the keyframe decision:
@@ -456,6 +460,7 @@ void odo_tracker_destroy(odo_tracker* t) {
     for (int i = 0; i < 2; i++)
       if (t->ev_lm[k][i]) cudaEventDestroy(t->ev_lm[k][i]);
   cudaFree(t->mem);
+  if (t->in_raw[0]) cudaFree(t->in_raw[0]);
   cudaFreeHost(t->h_state[0]);
   for (int k = 0; k < 2; k++) {
     for (int i = 0; i <= ODO_N_STAGES; i++)
@@ -520,6 +525,76 @@ int odo_tracker_step_u8(odo_tracker* t, const uint8_t* const* left, const uint8_
                         float* pose_kf, int* is_keyframe, int* status) {
   if (!t || t->n_enqueued != t->n_collected) return -1;
   if (tracker_enqueue<uint8_t>(t, left, right) != 0) return -1;
+  return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
+}
+
+int odo_tracker_set_rectify(odo_tracker* t, const odo_camera* left, const odo_camera* right, int raw_w, int raw_h) {
+  if (!t || !left || !right || raw_w < 2 || raw_h < 2) return -1;
+  odo_ctx* c = t->c;
+  int lw = 0, lh = 0, rw = 0, rh = 0;
+  if (odo_camera_map_size(left, &lw, &lh) != 0 || odo_camera_map_size(right, &rw, &rh) != 0 || lw != t->w || lh != t->h ||
+      rw != t->w || rh != t->h) {
+    c->err = "tracker: the cameras must be configured for the tracker's image size";
+    return -1;
+  }
+  if (t->n_enqueued != t->n_collected) {
+    c->err = "tracker: frames in flight";
+    return -1;
+  }
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (t->in_raw[0]) cudaFree(t->in_raw[0]);
+  t->in_raw[0] = t->in_raw[1] = nullptr;
+  const size_t slot_b = al256((size_t)raw_w * raw_h * t->n * 2);
+  ODO_CUDA_OK(c, cudaMalloc(&t->in_raw[0], slot_b * 2));
+  t->in_raw[1] = t->in_raw[0] + slot_b;
+  t->cam[0] = left;
+  t->cam[1] = right;
+  t->raw_w = raw_w;
+  t->raw_h = raw_h;
+  return 0;
+}
+
+int odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, const uint8_t* const* right_raw) {
+  if (!t || !left_raw || !right_raw) return -1;
+  odo_ctx* c = t->c;
+  if (!t->in_raw[0]) {
+    c->err = "tracker: odo_tracker_set_rectify has not run";
+    return -1;
+  }
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  if (t->n_enqueued - t->n_collected >= 2) {
+    c->err = "tracker: two frames are already in flight, collect one first";
+    return -1;
+  }
+  const int slot = (int)(t->n_enqueued & 1);
+  if (t->n_enqueued >= 2) ODO_CUDA_OK(c, cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[slot], 0));
+  const size_t rpx = (size_t)t->raw_w * t->raw_h;
+  uint8_t* rawL = t->in_raw[slot];
+  uint8_t* rawR = t->in_raw[slot] + rpx * t->n;
+  for (int b = 0; b < t->n; b++) {
+    ODO_CUDA_OK(c, cudaMemcpyAsync(rawL + rpx * b, left_raw[b], rpx, cudaMemcpyHostToDevice, t->copy_stream));
+    ODO_CUDA_OK(c, cudaMemcpyAsync(rawR + rpx * b, right_raw[b], rpx, cudaMemcpyHostToDevice, t->copy_stream));
+  }
+  ODO_CUDA_OK(c, cudaEventRecord(t->ev_copied[slot], t->copy_stream));
+  ODO_CUDA_OK(c, cudaStreamWaitEvent(c->stream, t->ev_copied[slot], 0));
+  // UndistortRectify (src/camera.cpp:72-83, border 0) + convertTo(CV_32F): the left eye as float, the right eye as
+  // float and as u8 (the depth refinement reads the raw right frame through its u8 plane)
+  uint8_t* R8 = t->in_u8[slot] + (size_t)t->n * t->npx;
+  if (launch_remap(c, t->cam[0], rawL, 1, t->raw_w, t->raw_h, (int64_t)rpx, t->in_left[slot], nullptr, t->npx, t->n, 0.0) != 0 ||
+      launch_remap(c, t->cam[1], rawR, 1, t->raw_w, t->raw_h, (int64_t)rpx, t->in_right[slot], R8, t->npx, t->n, 0.0) != 0) {
+    c->err = "tracker: remap launch failed";
+    return -1;
+  }
+  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, R8) != 0) return -1;
+  t->n_enqueued++;
+  return 0;
+}
+
+int odo_tracker_step_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, const uint8_t* const* right_raw,
+                            float* pose_abs, float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || t->n_enqueued != t->n_collected) return -1;
+  if (odo_tracker_enqueue_raw_u8(t, left_raw, right_raw) != 0) return -1;
   return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 

@@ -290,6 +290,42 @@ def compute_depth(L, R, p: DepthParams):
     return rc, val, disp, dep, st
 
 
+def camera_intrinsic_pyramid(P34, levels):
+    """ConfigureCamera's per-level (fx, fy, cx, cy, f_theta), src/camera.cpp:44-66."""
+    P = np.ascontiguousarray(P34, np.float64).reshape(12)
+    out = np.empty((levels, 5), np.float64)
+    lib().orc_camera_intrinsic_pyramid(_p(P, C.c_double), levels, _p(out, C.c_double))
+    return out
+
+
+def init_undistort_rectify_map(K, dist, R, P34, size):
+    """cv::initUndistortRectifyMap(..., CV_32FC1) -> (mapx, mapy); size = (w, h)."""
+    w, h = size
+    K, dist, R, P = [np.ascontiguousarray(a, np.float64).ravel() for a in (K, dist, R, P34)]
+    mx, my = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+    rc = lib().orc_init_undistort_rectify_map(_p(K, C.c_double), _p(dist, C.c_double), _p(R, C.c_double),
+                                              _p(P, C.c_double), w, h, _p(mx), _p(my))
+    if rc != 0:
+        raise ValueError("singular rectification")
+    return mx, my
+
+
+def remap_bilinear(src, mapx, mapy, cval=0):
+    """cv::remap(src, mapx, mapy, INTER_LINEAR, BORDER_CONSTANT, cval) for u8 or float32 sources."""
+    mapx, mapy = _f32(mapx), _f32(mapy)
+    dh, dw = mapx.shape
+    sh, sw = src.shape
+    if src.dtype == np.uint8:
+        src = np.ascontiguousarray(src)
+        dst = np.empty((dh, dw), np.uint8)
+        lib().orc_remap_bilinear_u8(_p(src, C.c_uint8), sw, sh, _p(mapx), _p(mapy), dw, dh, int(cval), _p(dst, C.c_uint8))
+    else:
+        src = _f32(src)
+        dst = np.empty((dh, dw), np.float32)
+        lib().orc_remap_bilinear_f32(_p(src), sw, sh, _p(mapx), _p(mapy), dw, dh, C.c_float(cval), _p(dst))
+    return dst
+
+
 def motion_magnitude(T):
     return float(lib().orc_motion_magnitude(_p(_colmajor(T))))
 

@@ -157,6 +157,18 @@ int orc_tracker_step(orc_tracker* t, const float* L, const float* R, float pose_
 /* motion magnitude of run_odometry_kitti_offline.cpp:145,254-257 */
 float orc_motion_magnitude(const float T_colmajor[16]);
 
+/* ---- undistort + rectify (src/camera.cpp:40-83; OpenCV arithmetic pinned to cv2 4.13.0) ---------- */
+/* ConfigureCamera's intrinsic pyramid, src/camera.cpp:44-66.  out: levels x 5 (fx fy cx cy f_theta) */
+void orc_camera_intrinsic_pyramid(const double P34[12], int levels, double* out);
+/* cv::initUndistortRectifyMap(K, (k1 k2 p1 p2), R, P, Size(w,h), CV_32FC1), src/camera.cpp:69 */
+int orc_init_undistort_rectify_map(const double K[9], const double dist[4], const double R[9], const double P34[12],
+                                   int w, int h, float* mapx, float* mapy);
+/* cv::remap(INTER_LINEAR, BORDER_CONSTANT, Scalar(cval)), src/camera.cpp:81, CV_8U and CV_32F sources */
+void orc_remap_bilinear_u8(const uint8_t* src, int sw, int sh, const float* mapx, const float* mapy, int dw, int dh,
+                           int cval, uint8_t* dst);
+void orc_remap_bilinear_f32(const float* src, int sw, int sh, const float* mapx, const float* mapy, int dw, int dh,
+                            float cval, float* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,15 +1,19 @@
 """Generate the golden vectors of tests/golden/ with the in-container cv2 (4.13.0).
 
 The reference calls cv::GaussianBlur / cv::pyrDown / cv::medianBlur (OpenCV, un-vendored); these
-fixtures pin the oracle's restatement of those primitives to what cv2 computes here.  Run from the
-repository root:  python tests/golden/make_golden.py
+fixtures pin the oracle's restatement of those primitives to what cv2 computes here.  cv2_camera.npz does
+the same for the undistort + rectify path (src/camera.cpp:40-83 and :84-170 of the reference:
+cv::stereoRectify, cv::initUndistortRectifyMap, cv::remap) on the reference's own calibration file.
+Run from the repository root:  python tests/golden/make_golden.py
 """
 import os
+import sys
 
 import cv2
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
 
 
 def main():
@@ -31,5 +35,44 @@ def main():
     print("wrote", os.path.join(HERE, "cv2_primitives.npz"))
 
 
+from camera_patterns import (CAM0_DIST, CAM0_INTR, CAM1_DIST, CAM1_INTR, RAW_SIZE, T_CN_CNM1, digest, kmat,  # noqa: E402
+                             raw_pattern_f32, raw_pattern_u8, stress_maps)
+
+
+def camera():
+    K0, K1 = kmat(CAM0_INTR), kmat(CAM1_INTR)
+    D0, D1 = np.array(CAM0_DIST), np.array(CAM1_DIST)
+    T = np.array(T_CN_CNM1)
+    R, t = T[:, :3].copy(), T[:, 3:].copy()
+    out = {"cv2_version": np.array(cv2.__version__), "K0": K0, "K1": K1, "D0": D0, "D1": D1, "R": R, "t": t}
+    # SetUpStereoCameraSystem, src/camera.cpp:139-141
+    R1, R2, P1, P2, Q, roi1, roi2 = cv2.stereoRectify(K0, D0, K1, D1, RAW_SIZE, R, t, flags=cv2.CALIB_ZERO_DISPARITY,
+                                                      alpha=1, newImageSize=RAW_SIZE)
+    out.update(R1=R1, R2=R2, P1=P1, P2=P2, Q=Q, roi1=np.array(roi1), roi2=np.array(roi2))
+    src8, srcf = raw_pattern_u8(), raw_pattern_f32()
+    out["src8_sha"], out["srcf_sha"] = digest(src8), digest(srcf)
+    for name, K, D, Rr, P in (("left", K0, D0, R1, P1), ("right", K1, D1, R2, P2)):
+        # ConfigureCamera, src/camera.cpp:69
+        mx, my = cv2.initUndistortRectifyMap(K, D, Rr, P, RAW_SIZE, cv2.CV_32FC1)
+        out[f"{name}/mapx_sha"], out[f"{name}/mapy_sha"] = digest(mx), digest(my)
+        out[f"{name}/mapx_rows"], out[f"{name}/mapy_rows"] = mx[::16].copy(), my[::16].copy()
+        # UndistortRectify with its defaults, src/camera.cpp:72,81
+        for tag, src in (("u8", src8), ("f32", srcf)):
+            for cval in (0, 9):
+                d = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=cval)
+                out[f"{name}/remap_{tag}_c{cval}_sha"] = digest(d)
+                out[f"{name}/remap_{tag}_c{cval}_rows"] = d[::16].copy()
+    # maps that leave the image on every side, land on the last row / column and on exact texel centres
+    mx, my = stress_maps()
+    out["stress/maps_sha"] = digest(np.stack([mx, my]))
+    for tag, src in (("u8", src8), ("f32", srcf)):
+        d = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=9)
+        out[f"stress/remap_{tag}_sha"] = digest(d)
+        out[f"stress/remap_{tag}_rows"] = d[::16].copy()
+    np.savez_compressed(os.path.join(HERE, "cv2_camera.npz"), **out)
+    print("wrote", os.path.join(HERE, "cv2_camera.npz"))
+
+
 if __name__ == "__main__":
     main()
+    camera()
