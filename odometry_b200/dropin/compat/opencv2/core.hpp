@@ -15,6 +15,8 @@
 #ifndef CV_8U
 #define CV_8U 0
 #define CV_32F 5
+#define CV_64F 6
+#define CV_32FC1 CV_32F
 #endif
 
 namespace cv {
@@ -31,6 +33,15 @@ struct Size {
   int width, height;
   Size(int w = 0, int h = 0) : width(w), height(h) {}
 };
+
+struct Rect {
+  int x, y, width, height;
+  Rect(int x_ = 0, int y_ = 0, int w = 0, int h = 0) : x(x_), y(y_), width(w), height(h) {}
+};
+
+// the two imgproc constants CameraPyramid::UndistortRectify takes as defaults (include/camera.h:64 of the reference)
+enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
+enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1 };
 
 class Mat {
  public:
@@ -59,7 +70,7 @@ class Mat {
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type, Scalar(0)); }
 
   int type() const { return type_; }
-  size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+  size_t elemSize() const { return type_ == CV_64F ? 8 : (type_ == CV_32F ? 4 : 1); }
   size_t total() const { return (size_t)rows * cols; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   bool isContinuous() const { return true; }

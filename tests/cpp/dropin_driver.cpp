@@ -11,6 +11,17 @@
 //       frame 0 only: ComputeDepth + both pyramid classes + the free builders + the per-pixel inlines;
 //       out.bin : val (u8 W*H), disp, dep (f32 W*H), every image / depth pyramid level (f32), then
 //                 the free-function pyramids again, then 8 floats of inline results
+//   dropin_driver io <poses_in.txt> <n> <dir>
+//       host I/O of run_odometry_kitti_offline.cpp:286-473 (no GPU): reads n KITTI poses, writes them back to
+//       <dir>/poses_out.txt with save_txt's formatting, the mean translation error against a copy shifted by
+//       (0.3, 0, 0.4) to <dir>/err.txt, and one synthetic keyframe (gray / mask / disparity PGM) + keyframe ids
+//   dropin_driver camera <camchain.yaml> <rect.f64> <raw.u8> <out.bin>
+//       what test_camera_setup.cpp does, with the stereoRectify results read from rect.f64 (R1[9] P1[12] R2[9]
+//       P2[12] doubles) because the image has no calib3d: ReadStereoCalibrationFile, two CameraPyramids,
+//       ConfigureCamera, UndistortRectify of raw.u8 ([2][480][640] uint8; the right frame is also fed as CV_32F).
+//       out.bin : 2 x (K_raw[9], dist[4], sensor w h, pixels_per_mm x y, resolution w h as doubles),
+//                 T[3] R[9] doubles, 2 x 4 levels x (fx fy cx cy f_theta) doubles, 2 x 4 floats fx_float..cy_float(1),
+//                 left u8 rectified [480][640], right u8 rectified, right f32 rectified
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +31,9 @@
 #include <tuple>
 #include <vector>
 
+#include <camera.h>
 #include <depth_estimate.h>
+#include <kitti_io.h>
 #include <image_processing_global.h>
 #include <image_pyramid.h>
 #include <lm_optimizer.h>
@@ -213,7 +226,104 @@ static int Units(const char* frames_path, int w, int h, const char* out_path) {
   return 0;
 }
 
+static int Camera(const char* yaml, const char* rect_path, const char* raw_path, const char* out_path) {
+  const std::vector<unsigned char> rect = ReadAll(rect_path), raw = ReadAll(raw_path);
+  if (rect.size() != 42 * sizeof(double) || raw.size() != (size_t)2 * 640 * 480) return 2;
+  FILE* out = std::fopen(out_path, "wb");
+  if (!out) return 2;
+  const int levels = 4;
+  // SetUpStereoCameraSystem, src/camera.cpp:86-137
+  cv::Mat K[2] = {cv::Mat(3, 3, CV_64F), cv::Mat(3, 3, CV_64F)}, D[2] = {cv::Mat(1, 4, CV_64F), cv::Mat(1, 4, CV_64F)};
+  cv::Mat Rlr(3, 3, CV_64F), Tlr(3, 1, CV_64F);
+  double sw[2], sh[2];
+  int rw = 0, rh = 0;
+  odometry::ReadStereoCalibrationFile(yaml, K[0], K[1], D[0], D[1], Rlr, Tlr, sw[0], sh[0], sw[1], sh[1], rw, rh);
+  std::shared_ptr<odometry::CameraPyramid> cam[2];
+  for (int k = 0; k < 2; k++)
+    cam[k] = std::make_shared<odometry::CameraPyramid>(levels, K[k].at<double>(0, 0), K[k].at<double>(1, 1), K[k].at<double>(0, 1),
+                                                       K[k].at<double>(0, 2), K[k].at<double>(1, 2), D[k].at<double>(0, 0),
+                                                       D[k].at<double>(0, 1), D[k].at<double>(0, 2), D[k].at<double>(0, 3),
+                                                       sw[k], sh[k], rw, rh);
+  // what test_camera_setup.cpp:24-58 prints
+  for (int k = 0; k < 2; k++) {
+    WriteMat(out, cam[k]->get_intrinsic_raw());
+    WriteMat(out, cam[k]->get_distortion_coeff());
+    const double v[6] = {cam[k]->sensor_w_double(), cam[k]->sensor_h_double(), cam[k]->pixels_per_mm_x_double(),
+                         cam[k]->pixels_per_mm_y_double(), (double)cam[k]->resolution_raw_w(), (double)cam[k]->resolution_raw_h()};
+    std::fwrite(v, sizeof(double), 6, out);
+  }
+  WriteMat(out, Tlr);
+  WriteMat(out, Rlr);
+  const double* r = reinterpret_cast<const double*>(rect.data());
+  const cv::Size img_size(640, 480);
+  for (int k = 0; k < 2; k++) {
+    cv::Mat R(3, 3, CV_64F, (void*)(r + 21 * k)), P(3, 4, CV_64F, (void*)(r + 21 * k + 9));
+    cam[k]->ConfigureCamera(R, P, img_size);  // src/camera.cpp:148-149
+  }
+  for (int k = 0; k < 2; k++)
+    for (int l = 0; l < levels; l++) {
+      const double v[5] = {cam[k]->fx_double(l), cam[k]->fy_double(l), cam[k]->cx_double(l), cam[k]->cy_double(l),
+                           cam[k]->f_theta_double(l)};
+      std::fwrite(v, sizeof(double), 5, out);
+    }
+  for (int k = 0; k < 2; k++) {
+    const float v[4] = {cam[k]->fx_float(1), cam[k]->fy_float(1), cam[k]->cx_float(1), cam[k]->cy_float(1)};
+    std::fwrite(v, sizeof(float), 4, out);
+  }
+  cv::Mat rawL(480, 640, CV_8U, (void*)raw.data()), rawR(480, 640, CV_8U, (void*)(raw.data() + 640 * 480)), rawRf, dst;
+  if (cam[0]->UndistortRectify(rawL, dst) != 0) return 3;
+  WriteMat(out, dst);
+  if (cam[1]->UndistortRectify(rawR, dst) != 0) return 3;
+  WriteMat(out, dst);
+  rawR.convertTo(rawRf, CV_32F);
+  cv::Mat dstf;
+  if (cam[1]->UndistortRectify(rawRf, dstf, cv::INTER_LINEAR, cv::BORDER_CONSTANT, cv::Scalar(9)) != 0) return 3;
+  WriteMat(out, dstf);
+  // the reference's size lock (src/camera.cpp:75-78) and the unsupported modes fail with -1
+  cv::Mat small(100, 100, CV_8U, cv::Scalar(0));
+  if (cam[0]->UndistortRectify(small, dst) != -1) return 4;
+  if (cam[0]->UndistortRectify(rawL, dst, cv::INTER_NEAREST) != -1) return 4;
+  std::fclose(out);
+  return 0;
+}
+
+static int Io(const char* poses_in, int n, const char* dir) {
+  namespace io = odometry::kitti_io;
+  std::vector<io::Pose34> gt, pred;
+  if (!io::LoadPoses(poses_in, (size_t)n, gt)) return 2;
+  if (io::LoadPoses(poses_in, (size_t)n + 1000, pred)) return 3;  // short file -> false
+  const std::string d(dir);
+  if (!io::SavePoses(d + "/poses_out.txt", gt)) return 2;
+  pred = gt;
+  for (io::Pose34& p : pred) {
+    p.m[3] += 0.3f;
+    p.m[11] += 0.4f;
+  }
+  std::vector<float> per;
+  const float e = io::TranslationError(gt, pred, (size_t)n, &per);
+  FILE* f = std::fopen((d + "/err.txt").c_str(), "w");
+  std::fprintf(f, "%.6f %zu\n", e, per.size());
+  std::fclose(f);
+  Affine4f T = Affine4f::Identity();
+  T(0, 3) = 1.5f; T(1, 2) = -0.25f;
+  const io::Pose34 p = io::FromAffine(T);
+  if (p.m[3] != 1.5f || p.m[6] != -0.25f || p.m[0] != 1.0f) return 4;
+  const int w = 8, h = 4;
+  cv::Mat img(h, w, CV_32F), dep(h, w, CV_32F), mask(h, w, CV_8U, cv::Scalar(0));
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      img.at<float>(y, x) = 40.0f * x - 20.0f + 0.5f * y;
+      dep.at<float>(y, x) = 0.01f * (x + 1) * (y + 1);
+      mask.at<uint8_t>(y, x) = (uint8_t)((x + y) & 1);
+    }
+  if (!io::SaveKeyframe(d, 3, img, dep, mask)) return 2;
+  if (!io::SaveKeyframeIds(d + "/keyframe_id.txt", {0, 7, 19})) return 2;
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 5 && std::string(argv[1]) == "io") return Io(argv[2], std::atoi(argv[3]), argv[4]);
+  if (argc >= 6 && std::string(argv[1]) == "camera") return Camera(argv[2], argv[3], argv[4], argv[5]);
   if (argc >= 7 && std::string(argv[1]) == "track")
     return Track(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), argv[6]);
   if (argc >= 6 && std::string(argv[1]) == "units")

@@ -45,6 +45,17 @@ def test_dropin_exports_the_reference_class_interface(dropin):
     assert "odometry::LevenbergMarquardtOptimizer::LevenbergMarquardtOptimizer(float, float, std::vector<int" in syms
 
 
+def test_dropin_exports_the_camera_interface(dropin):
+    lib, _ = dropin
+    syms = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    for w in ["odometry::CameraPyramid::CameraPyramid(int, double, double, double, double, double, double, double, double, "
+              "double, double, double, int, int)",                                               # include/camera.h:37-38
+              "odometry::CameraPyramid::ConfigureCamera(cv::Mat const&, cv::Mat const&, cv::Size const&, int, bool)",  # :56-57
+              "odometry::CameraPyramid::UndistortRectify(cv::Mat const&, cv::Mat&, int, int, cv::Scalar const&)",   # :68
+              "odometry::SetUpStereoCameraSystem(", "odometry::ReadStereoCalibrationFile("]:   # :126-133
+        assert w in syms, f"missing from libodometry_dropin.so: {w}"
+
+
 def test_dropin_has_no_cpu_fallback(dropin, tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -152,3 +163,108 @@ def test_dropin_tracking_loop_matches_oracle(dropin, synth_data, tmp_path):
         assert got["n_valid"][k] >= 500
     assert n_kf >= 2
     t.close()
+
+
+def _write_camchain(path):
+    """the reference's calibration_file/camchain.yaml, re-emitted from the fixture constants"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import camera_patterns as cp
+    rows = "\n".join("  - " + repr(list(r)) for r in cp.T_CN_CNM1 + [[0.0, 0.0, 0.0, 1.0]])
+    txt = f"""cam0:
+  cam_overlaps: [1]
+  camera_model: pinhole
+  distortion_coeffs: {cp.CAM0_DIST!r}
+  distortion_model: radtan
+  intrinsics: {cp.CAM0_INTR!r}
+  resolution: [640, 482]
+  sensor_size: [5.76, 4.29]
+  rostopic: /cam0/image_raw
+cam1:
+  T_cn_cnm1:
+{rows}
+  cam_overlaps: [0]
+  camera_model: pinhole
+  distortion_coeffs: {cp.CAM1_DIST!r}
+  distortion_model: radtan
+  intrinsics: {cp.CAM1_INTR!r}
+  resolution: [640, 482]
+  sensor_size: [5.76, 4.29]
+  rostopic: /cam1/image_raw
+"""
+    open(path, "w").write(txt)
+    return cp
+
+
+@pytest.mark.gpu
+def test_dropin_camera_setup_and_rectification(dropin, tmp_path):
+    """test_camera_setup.cpp against the drop-in: calibration file -> CameraPyramid x2 -> ConfigureCamera ->
+    UndistortRectify, checked against the cv2 golden vectors (tests/golden/cv2_camera.npz)."""
+    _, driver = dropin
+    cp = _write_camchain(tmp_path / "camchain.yaml")
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cv2_camera.npz"))
+    np.concatenate([G["R1"].ravel(), G["P1"].ravel(), G["R2"].ravel(), G["P2"].ravel()]).astype(np.float64).tofile(tmp_path / "rect.f64")
+    src8 = cp.raw_pattern_u8()
+    np.stack([src8, src8]).tofile(tmp_path / "raw.u8")
+    r = subprocess.run([driver, "camera", str(tmp_path / "camchain.yaml"), str(tmp_path / "rect.f64"), str(tmp_path / "raw.u8"),
+                        str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(tmp_path / "o.bin", "rb").read()
+    off = 0
+
+    def take(n, dt):
+        nonlocal off
+        a = np.frombuffer(raw, dt, n, off)
+        off += n * np.dtype(dt).itemsize
+        return a
+
+    for k, (K, D) in enumerate((("K0", "D0"), ("K1", "D1"))):
+        assert np.array_equal(take(9, np.float64).reshape(3, 3), G[K])
+        assert np.array_equal(take(4, np.float64), G[D])
+        assert np.array_equal(take(6, np.float64), [5.76, 4.29, 640 / 5.76, 482 / 4.29, 640, 482])
+    assert np.array_equal(take(3, np.float64), G["t"].ravel())
+    assert np.array_equal(take(9, np.float64).reshape(3, 3), G["R"])
+    want = [oracle.camera_intrinsic_pyramid(G[P], 4) for P in ("P1", "P2")]
+    for k in range(2):
+        assert np.array_equal(take(20, np.float64).reshape(4, 5), want[k])
+    for k in range(2):
+        assert np.array_equal(take(4, np.float32), want[k][1, :4].astype(np.float32))
+    npx = 640 * 480
+    left8 = take(npx, np.uint8).reshape(480, 640)
+    right8 = take(npx, np.uint8).reshape(480, 640)
+    rightf = take(npx, np.float32).reshape(480, 640)
+    assert str(cp.digest(left8)) == str(G["left/remap_u8_c0_sha"])
+    assert str(cp.digest(right8)) == str(G["right/remap_u8_c0_sha"])
+    mx, my = oracle.init_undistort_rectify_map(G["K1"], G["D1"], G["R2"], G["P2"], cp.RAW_SIZE)
+    assert np.array_equal(rightf, oracle.remap_bilinear(src8.astype(np.float32), mx, my, 9))
+    assert off == len(raw)
+
+
+def test_dropin_kitti_io_round_trip(dropin, tmp_path):
+    """load_gt_pose / save_txt / eval_pose / save_to_vis of run_odometry_kitti_offline.cpp:286-473 (host only)."""
+    _, driver = dropin
+    rng = np.random.default_rng(1)
+    poses = rng.normal(size=(5, 12)).astype(np.float32) * 10
+    with open(tmp_path / "in.txt", "w") as f:
+        for p in poses:
+            f.write(" ".join("%e" % v for v in p) + "\n")   # the devkit writes scientific notation
+    r = subprocess.run([driver, "io", str(tmp_path / "in.txt"), "5", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    back = np.loadtxt(tmp_path / "poses_out.txt", dtype=np.float64)
+    lines = open(tmp_path / "poses_out.txt").read().splitlines()
+    assert len(lines) == 5 and all(len(l.split(" ")) == 12 for l in lines)
+    assert lines[0].split(" ")[0] == "%f" % np.float32(float("%e" % poses[0, 0]))  # std::to_string(float) == "%f"
+    assert np.allclose(back, poses, atol=1e-6 + 1e-6 * np.abs(poses).max())
+    err, n = open(tmp_path / "err.txt").read().split()
+    assert float(err) == pytest.approx(0.5, abs=1e-5) and int(n) == 5
+    y, x = np.mgrid[0:4, 0:8]
+    g = open(tmp_path / "gray_3.pgm", "rb").read()
+    assert g.startswith(b"P5\n8 4\n255\n")
+    want = np.clip(np.rint((40.0 * x - 20.0 + 0.5 * y).astype(np.float32)), 0, 255).astype(np.uint8)
+    assert np.array_equal(np.frombuffer(g[-32:], np.uint8).reshape(4, 8), want)
+    m = np.frombuffer(open(tmp_path / "mask_3.pgm", "rb").read()[-32:], np.uint8).reshape(4, 8)
+    assert np.array_equal(m, ((x + y) & 1).astype(np.uint8))
+    d = np.frombuffer(open(tmp_path / "disparity_3.pgm", "rb").read()[-64:], ">u2").reshape(4, 8)
+    dep = (np.float32(0.01) * (x + 1).astype(np.float32) * (y + 1).astype(np.float32)).astype(np.float32)
+    assert np.array_equal(d, np.where(m != 0, (np.float32(386.1448) * dep).astype(np.uint16), 0))
+    assert open(tmp_path / "keyframe_id.txt").read().split() == ["0", "7", "19"]
