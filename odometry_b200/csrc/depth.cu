@@ -291,14 +291,18 @@ template <> struct DispTraits<false> {
 
 // PITCH: shared-memory row pitch in elements (W + 12 <= PITCH: 2 guard columns + 16-byte staging); staged column c of image row r lives at
 // rows[r * PITCH + c + 2] so that the taps at c - 2 of the first candidate stay inside the row.
-template <bool QPATH, int PITCH>
+// PRUNE (integer path only): scan the candidates from the pixel towards the left border and reject a whole chunk of
+// 32 candidates x 4 pixels from a 4-tap partial cost -- see the comment at the loop.
+template <bool QPATH, int PITCH, bool PRUNE>
 __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W, int H, odo_depth_params p, DepthWork d,
                                                                           int q_eligible, int pack_ok) {
   typedef typename DispTraits<QPATH>::elem elem_t;
   extern __shared__ __align__(16) unsigned char s_raw[];
   elem_t* s_rows = reinterpret_cast<elem_t*>(s_raw);                       // [5][PITCH]
   int* s_er = reinterpret_cast<int*>(s_raw + sizeof(elem_t) * 5 * PITCH);   // [PITCH]   (QPATH only)
-  uint16_t* s_xs = reinterpret_cast<uint16_t*>(s_raw + sizeof(elem_t) * 5 * PITCH + (QPATH ? sizeof(int) * PITCH : 0));
+  int* s_erT = s_er + PITCH;                                                // [PITCH]   (QPATH && PRUNE only)
+  uint16_t* s_xs = reinterpret_cast<uint16_t*>(s_raw + sizeof(elem_t) * 5 * PITCH +
+                                               (QPATH ? sizeof(int) * PITCH * (PRUNE ? 2 : 1) : 0));
   __shared__ int s_w[kDispWarps];
   const int b = blockIdx.y;
   const bool fast = q_eligible && d.exact[b] != 0;
@@ -351,7 +355,12 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
       const uint16_t* c = c0 + cx;
       const int t0 = c[2 * PITCH], t1 = c[PITCH - 1], t2 = c[2], t3 = c[0], t4 = c[-2], t5 = c[-PITCH + 1],
                 t6 = c[-PITCH - 1], t7 = c[-2 * PITCH];
-      s_er[cx] = t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6 + t7 * t7;
+      if (PRUNE) {  // energies of the two tap halves: T = {0, 2, 3, 4} (first pass), U = {1, 5, 6, 7}
+        s_erT[cx] = t0 * t0 + t2 * t2 + t3 * t3 + t4 * t4;
+        s_er[cx] = t1 * t1 + t5 * t5 + t6 * t6 + t7 * t7;
+      } else {
+        s_er[cx] = t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6 + t7 * t7;
+      }
     }
   } else {
     const float* src = d.blurR + b * npx + (int64_t)(y - 2) * W;
@@ -397,36 +406,122 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
         El[i] = e;
         best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
       }
-      const uint16_t* q_c = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2 + rx;
-      const int* q_e = s_er + rx;
-      // candidates below the smallest x of the group are candidates of every pixel: no range test
-      for (; rx < xmin; rx += 32, q_c += 32, q_e += 32) {
-        const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
-                  r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
-        const int ne = -q_e[0];
+      if (PRUNE) {
+        // The result only needs the minimum of the cost and, among equal costs, the smallest column (:382-386), so the
+        // scan order is free: walk DOWN from the pixel.  The true match lies within the first chunks (disparities are
+        // small against the row length); once it is known, a candidate whose 4-tap partial cost
+        // sum_T (l - r)^2 <= sum_all (l - r)^2 already exceeds the best full cost of the warp cannot win and its other
+        // four taps are never loaded or multiplied.  In the maximised form: acc_T = 2 sum_T l r - Er_T is compared with
+        // thr = best - El_U (El_U: the pixel's own energy over the other taps).  The decision is per pixel and
+        // warp-uniform (vote), thresholds are refreshed by a REDUX.MAX whenever a lane improves; ties (>=) move to the
+        // smaller column because the walk descends.  A stale threshold only prunes less, never wrongly.
+        int ElU[kDispP], thr[kDispP];
 #pragma unroll
         for (int i = 0; i < kDispP; i++) {
-          int acc = ne + l2[i][0] * r0;
-          acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
-          acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
-          if (acc > best[i]) {  // strict, ascending rx: the FIRST minimum stays (:382-386)
-            best[i] = acc;
-            brx[i] = rx;
+          const uint16_t* c = lq + max(xs[i], 2);
+          const int u1 = c[QP - 1], u5 = c[-QP + 1], u6 = c[-QP - 1], u7 = c[-2 * QP];
+          ElU[i] = u1 * u1 + u5 * u5 + u6 * u6 + u7 * u7;
+          thr[i] = -0x7fffffff - 1;
+          if (xs[i] == 0) best[i] = 0x7fffffff;  // absent pixel of a short group: never improves, never keeps a chunk alive
+        }
+        const uint16_t* c0 = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2;
+        // all eight taps of one chunk with the range test (the chunks that overlap the group's own pixels, and the
+        // last, partial chunk at the left border)
+        auto full_chunk = [&](int base) {
+          const int rxl = base - lane;
+          const bool ok = rxl >= bnd;
+          const int rc = ok ? rxl : bnd;
+          const int rcmp = ok ? rxl : 0x7fffffff;  // lanes left of the border and absent pixels (xs == 0) never qualify
+          const uint16_t* q_c = c0 + rc;
+          const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                    r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+          const int ne = -(s_erT[rc] + s_er[rc]);
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) {
+            int acc = ne + l2[i][0] * r0;
+            acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
+            acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+            if (rcmp < xs[i] && acc >= best[i]) {
+              best[i] = acc;
+              brx[i] = rxl;
+            }
+          }
+        };
+        auto refresh = [&]() {
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) {
+            const int wb = __reduce_max_sync(0xffffffffu, best[i]);
+            thr[i] = (wb == -0x7fffffff - 1) ? wb : wb - ElU[i];
+          }
+        };
+        int base = xg - 1;
+        for (; base >= xmin && base >= bnd; base -= 32) full_chunk(base);
+        refresh();
+        // chunks entirely left of every pixel of the group and entirely right of the border: no range test, pruned
+        const uint16_t* q_c = c0 + (base - lane);
+        const int* q_t = s_erT + (base - lane);
+        for (; base - 31 >= bnd; base -= 32, q_c -= 32, q_t -= 32) {
+          const int r0 = q_c[2 * PITCH], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2];
+          const int neT = -q_t[0];
+          int accT[kDispP];
+          bool lv = false;
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) {
+            int a = neT + l2[i][0] * r0;
+            a += l2[i][2] * r2; a += l2[i][3] * r3; a += l2[i][4] * r4;
+            accT[i] = a;
+            lv |= a >= thr[i];
+          }
+          if (__any_sync(0xffffffffu, lv)) {
+            const int r1 = q_c[PITCH - 1], r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+            const int neU = -s_er[base - lane];
+            bool up = false;
+#pragma unroll
+            for (int i = 0; i < kDispP; i++) {
+              int acc = accT[i] + neU;
+              acc += l2[i][1] * r1; acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+              if (acc >= best[i]) {
+                best[i] = acc;
+                brx[i] = base - lane;
+                up = true;
+              }
+            }
+            if (__any_sync(0xffffffffu, up)) refresh();
           }
         }
-      }
-      for (; rx < xg; rx += 32, q_c += 32, q_e += 32) {
-        const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
-                  r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
-        const int ne = -q_e[0];
+        if (base >= bnd) full_chunk(base);
+      } else {
+        const uint16_t* q_c = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2 + rx;
+        const int* q_e = s_er + rx;
+        // candidates below the smallest x of the group are candidates of every pixel: no range test
+        for (; rx < xmin; rx += 32, q_c += 32, q_e += 32) {
+          const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                    r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+          const int ne = -q_e[0];
 #pragma unroll
-        for (int i = 0; i < kDispP; i++) {
-          int acc = ne + l2[i][0] * r0;
-          acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
-          acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
-          if (rx < xs[i] && acc > best[i]) {
-            best[i] = acc;
-            brx[i] = rx;
+          for (int i = 0; i < kDispP; i++) {
+            int acc = ne + l2[i][0] * r0;
+            acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
+            acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+            if (acc > best[i]) {  // strict, ascending rx: the FIRST minimum stays (:382-386)
+              best[i] = acc;
+              brx[i] = rx;
+            }
+          }
+        }
+        for (; rx < xg; rx += 32, q_c += 32, q_e += 32) {
+          const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
+                    r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
+          const int ne = -q_e[0];
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) {
+            int acc = ne + l2[i][0] * r0;
+            acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
+            acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
+            if (rx < xs[i] && acc > best[i]) {
+              best[i] = acc;
+              brx[i] = rx;
+            }
           }
         }
       }
@@ -929,21 +1024,25 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
   c->launches++;
 }
 
-template <bool QPATH, int PITCH>
+template <bool QPATH, int PITCH, bool PRUNE = false>
 static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params& p, const DepthWork& d, int batch,
                                int q_eligible) {
+  if (QPATH && !PRUNE && !std::getenv("ODO_DISP_NOPRUNE")) {  // default for the integer path: the pruned scan
+    launch_disparity_t<QPATH, PITCH, QPATH>(c, w, h, p, d, batch, q_eligible);
+    return;
+  }
   const size_t esz = QPATH ? sizeof(uint16_t) : sizeof(float);
-  const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH : 0) + sizeof(uint16_t) * PITCH;
+  const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH * (PRUNE ? 2 : 1) : 0) + sizeof(uint16_t) * PITCH;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_disparity<QPATH, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_disparity<QPATH, PITCH, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   // one-instruction warp argmin on packed (cost, column) keys: needs 256 * ssd_th below the clamp (see kernel)
   const int key_bits = (PITCH <= 2048) ? 11 : 12;
   const int pack_ok = (QPATH && p.ssd_th * 256.0f < (float)((1 << (31 - key_bits)) - 1)) ? 1 : 0;
-  k_disparity<QPATH, PITCH><<<dim3(h - 2 * p.boundary, batch), kDispThreads, smem, c->stream>>>(w, h, p, d, q_eligible,
-                                                                                               pack_ok);
+  k_disparity<QPATH, PITCH, PRUNE><<<dim3(h - 2 * p.boundary, batch), kDispThreads, smem, c->stream>>>(w, h, p, d, q_eligible,
+                                                                                                      pack_ok);
   c->launches++;
 }
 
