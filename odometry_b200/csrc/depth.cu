@@ -300,10 +300,14 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
   extern __shared__ __align__(16) unsigned char s_raw[];
   elem_t* s_rows = reinterpret_cast<elem_t*>(s_raw);                       // [5][PITCH]
   int* s_er = reinterpret_cast<int*>(s_raw + sizeof(elem_t) * 5 * PITCH);   // [PITCH]   (QPATH only)
-  int* s_erT = s_er + PITCH;                                                // [PITCH]   (QPATH && PRUNE only)
+  // PRUNE: the same region holds one 16-byte record per candidate column instead: the 8 taps as bytes (x, y),
+  // -(byte energy / 2) (z) and the full 12-bit energy (w) -- one LDS.128 per candidate in the pruned loop
+  uint4* s_rec = reinterpret_cast<uint4*>(s_er);                            // [PITCH]   (QPATH && PRUNE only)
   uint16_t* s_xs = reinterpret_cast<uint16_t*>(s_raw + sizeof(elem_t) * 5 * PITCH +
-                                               (QPATH ? sizeof(int) * PITCH * (PRUNE ? 2 : 1) : 0));
+                                               (QPATH ? sizeof(int) * PITCH * (PRUNE ? 4 : 1) : 0));
   __shared__ int s_w[kDispWarps];
+  __shared__ __align__(16) int s_l2[PRUNE ? kDispWarps * kDispP * 8 : 4];  // PRUNE: 2 * left taps of the warp's current group
+  __shared__ int4 s_grp[PRUNE ? kDispWarps * kDispP : 1];                  // PRUNE: per pixel of the group: El, El8, packed bytes
   const int b = blockIdx.y;
   const bool fast = q_eligible && d.exact[b] != 0;
   if (fast != QPATH) return;
@@ -355,9 +359,11 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
       const uint16_t* c = c0 + cx;
       const int t0 = c[2 * PITCH], t1 = c[PITCH - 1], t2 = c[2], t3 = c[0], t4 = c[-2], t5 = c[-PITCH + 1],
                 t6 = c[-PITCH - 1], t7 = c[-2 * PITCH];
-      if (PRUNE) {  // energies of the two tap halves: T = {0, 2, 3, 4} (first pass), U = {1, 5, 6, 7}
-        s_erT[cx] = t0 * t0 + t2 * t2 + t3 * t3 + t4 * t4;
-        s_er[cx] = t1 * t1 + t5 * t5 + t6 * t6 + t7 * t7;
+      if (PRUNE) {  // the taps again as bytes (q >> 4 = floor of the blurred value), packed for IDP4A, and their energy
+        const int b0 = t0 >> 4, b1 = t1 >> 4, b2 = t2 >> 4, b3 = t3 >> 4, b4 = t4 >> 4, b5 = t5 >> 4, b6 = t6 >> 4, b7 = t7 >> 4;
+        s_rec[cx] = make_uint4(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24), b4 | (b5 << 8) | (b6 << 16) | (b7 << 24),
+                               (unsigned)(-((b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3 + b4 * b4 + b5 * b5 + b6 * b6 + b7 * b7) >> 1)),
+                               (unsigned)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6 + t7 * t7));
       } else {
         s_er[cx] = t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3 + t4 * t4 + t5 * t5 + t6 * t6 + t7 * t7;
       }
@@ -392,104 +398,146 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
     if (QPATH) {
       constexpr int QP = PITCH;  // == q_pitch(W)
       const uint16_t* lq = d.qL + b * (int64_t)QP * H + (int64_t)y * QP;
-      int l2[kDispP][8], El[kDispP], best[kDispP];
+      int l2[PRUNE ? 1 : kDispP][8], El[kDispP], best[kDispP];
+      if (!PRUNE) {
 #pragma unroll
-      for (int i = 0; i < kDispP; i++) {
-        const uint16_t* c = lq + max(xs[i], 2);
-        const int t[8] = {c[2 * QP], c[QP - 1], c[2], c[0], c[-2], c[-QP + 1], c[-QP - 1], c[-2 * QP]};
-        int e = 0;
+        for (int i = 0; i < kDispP; i++) {
+          const uint16_t* c = lq + max(xs[i], 2);
+          const int t[8] = {c[2 * QP], c[QP - 1], c[2], c[0], c[-2], c[-QP + 1], c[-QP - 1], c[-2 * QP]};
+          int e = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          e += t[k] * t[k];
-          l2[i][k] = 2 * t[k];
+          for (int k = 0; k < 8; k++) {
+            e += t[k] * t[k];
+            l2[PRUNE ? 0 : i][k] = 2 * t[k];
+          }
+          El[i] = e;
+          best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
         }
-        El[i] = e;
-        best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
       }
       if (PRUNE) {
         // The result only needs the minimum of the cost and, among equal costs, the smallest column (:382-386), so the
         // scan order is free: walk DOWN from the pixel.  The true match lies within the first chunks (disparities are
-        // small against the row length); once it is known, a candidate whose 4-tap partial cost
-        // sum_T (l - r)^2 <= sum_all (l - r)^2 already exceeds the best full cost of the warp cannot win and its other
-        // four taps are never loaded or multiplied.  In the maximised form: acc_T = 2 sum_T l r - Er_T is compared with
-        // thr = best - El_U (El_U: the pixel's own energy over the other taps).  The decision is per pixel and
-        // warp-uniform (vote), thresholds are refreshed by a REDUX.MAX whenever a lane improves; ties (>=) move to the
-        // smaller column because the walk descends.  A stale threshold only prunes less, never wrongly.
-        int ElU[kDispP], thr[kDispP];
+        // small against the row length); once it is known almost every other candidate can be rejected from a cheap
+        // LOWER BOUND of its cost, and its eight 12-bit taps are never loaded or multiplied.  The bound works on the
+        // taps as bytes, l8 = q >> 4: |l - r| >= 16 (|l8 - r8| - 1), so with S = sum (l8 - r8)^2 over the 8 taps
+        //     256 SSD >= 256 (S - 2 sum |l8 - r8|) >= 256 (S - 2 sqrt(8 S))          (Cauchy-Schwarz)
+        // and a candidate with S > S_thr = (sqrt 8 + sqrt(8 + best / 256))^2 cannot beat `best`.  S = El8 + Er8 - 2 dot
+        // costs two IDP4A per pixel on one 16-byte shared-memory record per candidate (instead of 8 IMAD on 8 loads);
+        // in the maximised form acc8 = dot - floor(Er8 / 2) is compared with thr8 = floor((El8 - S_thr) / 2), both
+        // roundings on the safe side.  The decision is warp-uniform (one vote per chunk of 32 candidates x 4 pixels);
+        // thresholds are refreshed whenever the best of the warp improves; ties (>=) move to the smaller column because
+        // the walk descends.  A stale or loose threshold only prunes less, never wrongly.
+        //
+        // Group setup is lane-parallel: lane 8 i + k loads tap k of pixel i (one load per lane), the energies and the
+        // packed byte words are formed by shuffles, and the doubled 12-bit taps are parked in shared memory -- only the
+        // chunks that survive the bound need them, so they do not occupy 32 registers across the pruned loop.
+        unsigned la8[kDispP], lb8[kDispP];
+        int El8[kDispP], thr[kDispP], wbest[kDispP];  // wbest: best of the whole warp (uniform), thr: its byte-domain threshold
+        int El_mine, El8_mine;                       // of pixel (lane & 3): the threshold refresh is lane-parallel too
+        {
+          const int pi = lane >> 3, pk = lane & 7;
+          const int kk = g * kDispP + pi;
+          const int xl = (kk < n) ? (int)s_xs[kk] : 0;
+          const int dy = (int)((0x01122234u >> (4 * pk)) & 15u) - 2, dx = (int)((0x21302412u >> (4 * pk)) & 15u) - 2;
+          const int q = lq[max(xl, 2) + dy * QP + dx];
+          int e = q * q;
+          const int q8 = q >> 4;
+          int e8 = q8 * q8;
+          unsigned wd = (unsigned)q8 << (8 * (pk & 3));
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+            e8 += __shfl_xor_sync(0xffffffffu, e8, o);
+            if (o < 4) wd |= __shfl_xor_sync(0xffffffffu, wd, o);
+          }
+          const unsigned wo = __shfl_xor_sync(0xffffffffu, wd, 4);
+          __syncwarp();  // the previous group of this warp is done with s_l2 / s_grp
+          s_l2[wid * 32 + lane] = 2 * q;
+          if (pk == 0) s_grp[wid * kDispP + pi] = make_int4(e, e8, (int)wd, (int)wo);
+          __syncwarp();
+        }
 #pragma unroll
         for (int i = 0; i < kDispP; i++) {
-          const uint16_t* c = lq + max(xs[i], 2);
-          const int u1 = c[QP - 1], u5 = c[-QP + 1], u6 = c[-QP - 1], u7 = c[-2 * QP];
-          ElU[i] = u1 * u1 + u5 * u5 + u6 * u6 + u7 * u7;
-          thr[i] = -0x7fffffff - 1;
-          if (xs[i] == 0) best[i] = 0x7fffffff;  // absent pixel of a short group: never improves, never keeps a chunk alive
+          const int4 rec = s_grp[wid * kDispP + i];
+          El[i] = rec.x;
+          El8[i] = rec.y;
+          la8[i] = (unsigned)rec.z;
+          lb8[i] = (unsigned)rec.w;
+          best[i] = thr[i] = wbest[i] = -0x7fffffff - 1;
+          if (xs[i] == 0) best[i] = wbest[i] = 0x7fffffff;  // absent pixel of a short group: never improves, never keeps a chunk alive
         }
+        {
+          const int4 rec = s_grp[wid * kDispP + (lane & 3)];
+          El_mine = rec.x;
+          El8_mine = rec.y;
+        }
+        const volatile int4* l2s = reinterpret_cast<const volatile int4*>(s_l2 + wid * kDispP * 8);
         const uint16_t* c0 = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2;
-        // all eight taps of one chunk with the range test (the chunks that overlap the group's own pixels, and the
-        // last, partial chunk at the left border)
-        auto full_chunk = [&](int base) {
+        // all eight taps of one chunk with the range test (the chunks that overlap the group's own pixels, the chunks
+        // the bound could not reject, and the last, partial chunk at the left border)
+        auto full_chunk = [&](int base, bool ranged) -> bool {
           const int rxl = base - lane;
           const bool ok = rxl >= bnd;
           const int rc = ok ? rxl : bnd;
-          const int rcmp = ok ? rxl : 0x7fffffff;  // lanes left of the border and absent pixels (xs == 0) never qualify
+          const int rcmp = (ok || !ranged) ? rxl : 0x7fffffff;  // lanes left of the border and absent pixels (xs == 0) never qualify
           const uint16_t* q_c = c0 + rc;
           const int r0 = q_c[2 * PITCH], r1 = q_c[PITCH - 1], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2],
                     r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
-          const int ne = -(s_erT[rc] + s_er[rc]);
+          const int ne = -(int)s_rec[rc].w;
+          bool up = false;
 #pragma unroll
           for (int i = 0; i < kDispP; i++) {
-            int acc = ne + l2[i][0] * r0;
-            acc += l2[i][1] * r1; acc += l2[i][2] * r2; acc += l2[i][3] * r3; acc += l2[i][4] * r4;
-            acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
-            if (rcmp < xs[i] && acc >= best[i]) {
+            const int4 la = make_int4(l2s[2 * i].x, l2s[2 * i].y, l2s[2 * i].z, l2s[2 * i].w);
+            const int4 lb = make_int4(l2s[2 * i + 1].x, l2s[2 * i + 1].y, l2s[2 * i + 1].z, l2s[2 * i + 1].w);
+            int acc = ne + la.x * r0;
+            acc += la.y * r1; acc += la.z * r2; acc += la.w * r3; acc += lb.x * r4;
+            acc += lb.y * r5; acc += lb.z * r6; acc += lb.w * r7;
+            if ((!ranged || rcmp < xs[i]) && acc >= best[i]) {
               best[i] = acc;
               brx[i] = rxl;
+              up |= acc > wbest[i];  // only a new best of the WARP moves the threshold
             }
           }
+          return up;
         };
         auto refresh = [&]() {
+          int wsel = 0;
 #pragma unroll
           for (int i = 0; i < kDispP; i++) {
-            const int wb = __reduce_max_sync(0xffffffffu, best[i]);
-            thr[i] = (wb == -0x7fffffff - 1) ? wb : wb - ElU[i];
+            wbest[i] = __reduce_max_sync(0xffffffffu, best[i]);
+            wsel = ((lane & 3) == i) ? wbest[i] : wsel;
           }
+          // lane-parallel: lane l computes the threshold of pixel l & 3, a shuffle hands it to everybody
+          int t = wsel;  // nothing found yet (INT_MIN): keep everything; absent pixel (INT_MAX): reject everything
+          if (wsel != -0x7fffffff - 1 && wsel != 0x7fffffff) {
+            const float x = 8.0f + (float)(El_mine - wsel) * (1.0f / 256.0f);   // 8 + best SSD so far
+            const float rt = 2.8285f + x * rsqrtf(x);                            // MUFU.RSQ: 2^-22 relative, far inside the margin
+            const float sthr = fminf(rt * rt * 1.0001f + 2.0f, 1.0e9f);         // rounded up generously
+            t = (El8_mine - (int)sthr - 1) >> 1;                                 // floor((El8 - S_thr) / 2), arithmetic shift
+          }
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) thr[i] = __shfl_sync(0xffffffffu, t, i);
         };
         int base = xg - 1;
-        for (; base >= xmin && base >= bnd; base -= 32) full_chunk(base);
+        for (; base >= xmin && base >= bnd; base -= 32) full_chunk(base, true);
         refresh();
         // chunks entirely left of every pixel of the group and entirely right of the border: no range test, pruned
-        const uint16_t* q_c = c0 + (base - lane);
-        const int* q_t = s_erT + (base - lane);
-        for (; base - 31 >= bnd; base -= 32, q_c -= 32, q_t -= 32) {
-          const int r0 = q_c[2 * PITCH], r2 = q_c[2], r3 = q_c[0], r4 = q_c[-2];
-          const int neT = -q_t[0];
-          int accT[kDispP];
+        const uint4* q_p = s_rec + (base - lane);
+        for (; base - 31 >= bnd; base -= 32, q_p -= 32) {
+          const uint4 pk = q_p[0];
+          const int ne8 = (int)pk.z;
           bool lv = false;
 #pragma unroll
           for (int i = 0; i < kDispP; i++) {
-            int a = neT + l2[i][0] * r0;
-            a += l2[i][2] * r2; a += l2[i][3] * r3; a += l2[i][4] * r4;
-            accT[i] = a;
+            const int a = (int)__dp4a(lb8[i], pk.y, __dp4a(la8[i], pk.x, (unsigned)ne8));
             lv |= a >= thr[i];
           }
           if (__any_sync(0xffffffffu, lv)) {
-            const int r1 = q_c[PITCH - 1], r5 = q_c[-PITCH + 1], r6 = q_c[-PITCH - 1], r7 = q_c[-2 * PITCH];
-            const int neU = -s_er[base - lane];
-            bool up = false;
-#pragma unroll
-            for (int i = 0; i < kDispP; i++) {
-              int acc = accT[i] + neU;
-              acc += l2[i][1] * r1; acc += l2[i][5] * r5; acc += l2[i][6] * r6; acc += l2[i][7] * r7;
-              if (acc >= best[i]) {
-                best[i] = acc;
-                brx[i] = base - lane;
-                up = true;
-              }
-            }
+            const bool up = full_chunk(base, false);
             if (__any_sync(0xffffffffu, up)) refresh();
           }
         }
-        if (base >= bnd) full_chunk(base);
+        if (base >= bnd) full_chunk(base, true);
       } else {
         const uint16_t* q_c = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2 + rx;
         const int* q_e = s_er + rx;
@@ -1032,7 +1080,7 @@ static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params&
     return;
   }
   const size_t esz = QPATH ? sizeof(uint16_t) : sizeof(float);
-  const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH * (PRUNE ? 2 : 1) : 0) + sizeof(uint16_t) * PITCH;
+  const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH * (PRUNE ? 4 : 1) : 0) + sizeof(uint16_t) * PITCH;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_disparity<QPATH, PITCH, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
