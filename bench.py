@@ -51,9 +51,10 @@ def parse():
     ap.add_argument("--cpu-seqs", type=int, default=2, help="sequences of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="kitti", choices=["kitti", "4k"],
+    ap.add_argument("--workload", default="kitti", choices=["kitti", "4k", "rectify"],
                     help="kitti: the headline tracking step (BASELINE.json configs 3/4); 4k: config 5, 3840x2160 "
-                         "6-level pyramid + all-pixel dense LM alignment of each new frame against a keyframe")
+                         "6-level pyramid + all-pixel dense LM alignment of each new frame against a keyframe; "
+                         "rectify: the camera front end (SURVEY 8 f3), UndistortRectify of raw 640x480 stereo pairs")
     return ap.parse_args()
 
 
@@ -447,6 +448,197 @@ def run_4k(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload rectify: the camera front end.  A step = UndistortRectify (src/camera.cpp:72-83) of a batch
+# of raw 640x480 u8 stereo pairs into CV_32F rectified pairs (the convertTo of run_odometry_kitti_offline.cpp:348 fused),
+# with the reference's own calibration (calibration_file/camchain.yaml, values kept in tests/golden/camera_patterns.py)
+# and the stereoRectify results of the committed golden fixture.
+METRIC_RECT = "undistort+rectify stereo pairs/s (640x480 u8 raw -> CV_32F rectified, both eyes)"
+RW, RH = 640, 480
+
+
+def rectify_setup():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import camera_patterns as cp
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cv2_camera.npz"))
+    return cp, G
+
+
+def config_rect(args, pairs):
+    return {"workload": f"front end (SURVEY 8 f3): UndistortRectify of {pairs} raw 640x480 u8 stereo pairs per step per GPU into "
+                        "CV_32F, INTER_LINEAR / BORDER_CONSTANT, tables from ConfigureCamera on the reference's calibration file",
+            "pairs_per_gpu": pairs, "frame": f"{RW}x{RH}", "parallelism": f"independent pairs x{args.gpus} GPUs, no collective",
+            "l2": f"each step reads {pairs * 2 * RW * RH / 1e6:.0f} MB of fresh raw frames and writes {pairs * 8 * RW * RH / 1e6:.0f} MB (> 126 MB L2)"}
+
+
+def raw_pairs(n, seed):
+    rng = np.random.default_rng(20190117 + seed)
+    base = rng.integers(0, 256, (RH // 8 + 2, RW // 8 + 2)).astype(np.float32)
+    out = np.empty((n, 2, RH, RW), np.uint8)
+    yy, xx = np.mgrid[0:RH, 0:RW]
+    for i in range(n):
+        for e in range(2):
+            sh = (i * 7 + e * 3) % 8
+            out[i, e] = (base[(yy + sh) // 8, (xx + sh) // 8] * 0.75 + ((xx * 3 + yy * 5 + i) % 64)).astype(np.uint8)
+    return out
+
+
+def cpu_rectify_pairs_per_s(raw, maps, threads):
+    import oracle
+    n = raw.shape[0]
+    t0 = time.perf_counter()
+
+    def work(i):
+        for e in range(2):
+            oracle.remap_bilinear(raw[i, e], maps[e][0], maps[e][1], 0).astype(np.float32)
+
+    if threads == 1:
+        for i in range(n):
+            work(i)
+    else:
+        ths = [threading.Thread(target=lambda k=k: [work(i) for i in range(k, n, threads)]) for k in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference_rectify(args, rank):
+    if rank != 0:
+        return
+    import oracle
+    cp, G = rectify_setup()
+    maps = [oracle.init_undistort_rectify_map(G[K], G[D], G[R], G[P], cp.RAW_SIZE) for K, D, R, P in
+            (("K0", "D0", "R1", "P1"), ("K1", "D1", "R2", "P2"))]
+    cores = os.cpu_count() or 1
+    n = 16 * cores
+    raw = raw_pairs(n, 0)
+    K_steps = max(1, min(args.steps, 5))
+    cpu_rectify_pairs_per_s(raw[:cores], maps, cores)
+    t0 = time.perf_counter()
+    for _ in range(K_steps):
+        cpu_rectify_pairs_per_s(raw, maps, cores)
+    dt = time.perf_counter() - t0
+    v = n * K_steps / dt
+    line = {"impl": "reference", "metric": METRIC_RECT, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": K_steps,
+            "warmup": 1, "ms_per_step": dt / K_steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": config_rect(args, n),
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} pairs per step, one thread per logical core; the oracle's restatement of cv::remap "
+                                       "(the reference calls OpenCV here; oracle/camera.cpp is pinned bit-exactly to cv2 4.13.0)"},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_rectify(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from odometry_b200 import capi, shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    cp, G = rectify_setup()
+    stream = torch.cuda.current_stream(dev)
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+    cams = []
+    for Kk, D, R, P in (("K0", "D0", "R1", "P1"), ("K1", "D1", "R2", "P2")):
+        cam = capi.Camera(ctx, 4, G[Kk], G[D], sensor=(5.76, 4.29), resolution=(640, 482))
+        cam.configure(G[R], G[P], cp.RAW_SIZE)
+        cams.append(cam)
+    B = 256
+    nbuf = 3   # rotating input batches: every step reads raw frames that are not in L2
+    raw_np = raw_pairs(B, rank)
+    raws = [torch.from_numpy(np.roll(raw_np, k, axis=0).copy()).to(dev) for k in range(nbuf)]   # [B][2][H][W] u8
+    out = torch.empty((2, B, RH, RW), dtype=torch.float32, device=dev)
+    npx = RW * RH
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(i):
+        r = raws[i % nbuf]
+        for e in range(2):
+            cams[e].undistort_rectify_dev(r.data_ptr() + e * npx, True, RW, RH, 2 * npx, out[e].data_ptr(), False, npx, B)
+
+    def timed(fn):
+        shard.barrier(dev)
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        shard.barrier(dev)
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for i in range(Wm):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    l0 = ctx.launch_count()
+    sampler.start()
+    ms_total = timed(lambda: [step(Wm + i) for i in range(K)])
+    clocks = sampler.result()
+    launches = ctx.launch_count() - l0
+    value = world * B * K / (ms_total * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        ne = 16
+        host = torch.from_numpy(raw_np[:ne]).pin_memory()
+
+        def step_host():
+            for i in range(ne):
+                for e in range(2):
+                    cams[e].undistort_rectify(host[i, e].numpy(), out_dtype=np.float32)   # H2D + kernel + D2H inside the call
+
+        step_host()
+        ms = timed(lambda: [step_host() for _ in range(K)])
+        e2e = {"value": world * ne * K / (ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": ne * 2 * npx,
+               "d2h_bytes_per_step": ne * 2 * npx * 4, "ms_per_step": ms / K, "pairs_per_step": ne,
+               "host_buffers": "pinned u8 raw frames, pageable float32 results",
+               "api": "odo_camera_undistort_rectify (one synchronous call per image; the rectified CV_32F image is the result read back)"}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    launch_ms = ms_total / K / 2
+    alg = B * npx * (1 + 4) + 8 * npx      # raw u8 in, CV_32F out, the float2 table once per launch
+    ach = alg / (launch_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_remap<u8>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "launch_ms": launch_ms, "algorithmic_bytes_per_launch": alg,
+            "images_per_launch": B}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        maps = [c.maps() for c in cams]
+        n = 24
+        cpu_rectify_pairs_per_s(raw_np[:2], maps, 1)
+        v = cpu_rectify_pairs_per_s(raw_np[:n], maps, 1)
+        cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": f"{n} pairs, 1 thread; the oracle's restatement of cv::remap (pinned bit-exactly to cv2 4.13.0)"}
+        chk = out[0, 0].cpu().numpy()
+        ref0 = oracle.remap_bilinear(raws[(Wm + K - 1) % nbuf][0, 0].cpu().numpy(), maps[0][0], maps[0][1], 0).astype(np.float32)
+        roof["checked_against_oracle"] = bool(np.array_equal(chk, ref0))
+    if rank == 0:
+        line = {"metric": METRIC_RECT, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": config_rect(args, B), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "pairs_per_step": world * B}
+        print(json.dumps(line), flush=True)
+    for c in cams:
+        c.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -455,11 +647,16 @@ def main():
     if args.impl == "reference":
         if args.workload == "4k":
             run_reference_4k(args, rank)
+        elif args.workload == "rectify":
+            run_reference_rectify(args, rank)
         else:
             run_reference(args, rank, world)
         return
     if args.workload == "4k":
         run_4k(args, rank, local_rank, world)
+        return
+    if args.workload == "rectify":
+        run_rectify(args, rank, local_rank, world)
         return
 
     import torch
