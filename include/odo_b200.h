@@ -176,6 +176,9 @@ int  odo_camera_maps_download(odo_ctx* ctx, const odo_camera* cam, float* mapx, 
  * elements apart, runs on the context's stream and does not wait. */
 int  odo_camera_undistort_rectify(odo_ctx* ctx, const odo_camera* cam, const void* src, int src_type, int sw, int sh,
                                   void* dst, int dst_type, double border_value);
+/* n host images in, n host images out with ONE kernel launch and one wait (pin the host buffers for full PCIe speed) */
+int  odo_camera_undistort_rectify_batch(odo_ctx* ctx, const odo_camera* cam, const void* const* srcs, int src_type, int sw,
+                                        int sh, void* const* dsts, int dst_type, int n, double border_value);
 int  odo_camera_undistort_rectify_dev(odo_ctx* ctx, const odo_camera* cam, const void* src_dev, int src_type, int sw,
                                       int sh, int64_t src_stride, void* dst_dev, int dst_type, int64_t dst_stride,
                                       int batch, double border_value);

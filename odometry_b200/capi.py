@@ -57,6 +57,7 @@ EXPORTS = [
     "odo_camera_create", "odo_camera_destroy", "odo_camera_configure", "odo_camera_set_maps", "odo_camera_levels",
     "odo_camera_intrinsics", "odo_camera_raw", "odo_camera_lm_intrinsics", "odo_camera_map_size",
     "odo_camera_maps_download", "odo_camera_undistort_rectify", "odo_camera_undistort_rectify_dev",
+    "odo_camera_undistort_rectify_batch",
     "odo_tracker_set_rectify", "odo_tracker_enqueue_raw_u8", "odo_tracker_step_raw_u8",
 ]
 PIX_U8, PIX_F32 = 0, 5
@@ -99,6 +100,8 @@ def lib():
                                                    C.c_void_p, C.c_int, C.c_double]
         L.odo_camera_undistort_rectify_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                        C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double]
+        L.odo_camera_undistort_rectify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                         C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.odo_tracker_set_rectify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -365,6 +368,15 @@ class Camera:
         if rc != 0:
             raise OdoError(self.ctx.last_error())
         return dst
+
+    def undistort_rectify_batch_ptrs(self, src_ptrs, src_u8, sw, sh, dst_ptrs, dst_u8, border_value=0.0):
+        """n host images (raw addresses, ideally pinned) -> n host images: one launch, one wait."""
+        n = len(src_ptrs)
+        arr_t = C.c_void_p * n
+        rc = lib().odo_camera_undistort_rectify_batch(self.ctx.h, self.h, arr_t(*src_ptrs), PIX_U8 if src_u8 else PIX_F32, sw, sh,
+                                                      arr_t(*dst_ptrs), PIX_U8 if dst_u8 else PIX_F32, n, float(border_value))
+        if rc != 0:
+            raise OdoError(self.ctx.last_error())
 
     def undistort_rectify_dev(self, src_ptr, src_u8, sw, sh, src_stride, dst_ptr, dst_u8, dst_stride, batch, border_value=0.0):
         rc = lib().odo_camera_undistort_rectify_dev(self.ctx.h, self.h, C.c_void_p(src_ptr), PIX_U8 if src_u8 else PIX_F32,

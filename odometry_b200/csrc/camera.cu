@@ -23,7 +23,8 @@ struct odo_camera {
   double intr[ODO_MAX_LEVELS][5] = {{0}};  // fx fy cx cy f_theta per level (rectified)
   int device = -1;
   int map_w = 0, map_h = 0;
-  float2* map = nullptr;  // device, [map_h][map_w] (source x, source y)
+  float2* map = nullptr;  // device, [map_h][map_w] (source x, source y): rmap_[0], rmap_[1] interleaved
+  uint2* fix = nullptr;   // device, the same table as remap() uses it: x = ix | iy << 16 (saturated shorts), y = fa | fb << 8
   bool configured = false;
 };
 
@@ -55,6 +56,17 @@ __device__ __forceinline__ int cv_round(float v) {
   return (v >= -2147483648.0f && v < 2147483648.0f) ? __float2int_rn(v) : INT_MIN;
 }
 
+// the CV_32FC1 pair -> (CV_16SC2, CV_16UC1) conversion remap() applies before interpolating (INTER_TAB_SIZE = 32), done
+// once per table instead of once per frame
+__global__ void __launch_bounds__(256) k_fix_map(const float2* __restrict__ map, int64_t n, uint2* __restrict__ fix) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 m = map[i];
+  const int sx = cv_round(m.x * 32.0f), sy = cv_round(m.y * 32.0f);
+  const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));  // saturate_cast<short>
+  fix[i] = make_uint2(((unsigned)ix & 0xffffu) | ((unsigned)iy << 16), (unsigned)(sx & 31) | ((unsigned)(sy & 31) << 8));
+}
+
 template <typename T> struct RemapTraits;
 template <> struct RemapTraits<uint8_t> {
   typedef int acc;
@@ -73,7 +85,7 @@ constexpr int kRemapPx = 4;
 
 template <typename SrcT>
 __global__ void __launch_bounds__(128) k_remap(const SrcT* __restrict__ src, int64_t sstride, int sw, int sh,
-                                               const float2* __restrict__ map, int dw, int dh,
+                                               const uint2* __restrict__ map, int dw, int dh,
                                                float* __restrict__ dst_f, uint8_t* __restrict__ dst_8, int64_t dstride,
                                                typename RemapTraits<SrcT>::acc cval) {
   typedef typename RemapTraits<SrcT>::acc acc_t;
@@ -82,21 +94,20 @@ __global__ void __launch_bounds__(128) k_remap(const SrcT* __restrict__ src, int
   const SrcT* s = src + (int64_t)b * sstride;
   const size_t o = (size_t)y * dw + x0;
   const bool full = (x0 + kRemapPx <= dw) && ((o & 3) == 0);
-  float2 m[kRemapPx];
+  uint2 m[kRemapPx];
   if (full) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(map + o));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(map + o) + 1);
-    m[0] = make_float2(a.x, a.y); m[1] = make_float2(a.z, a.w); m[2] = make_float2(c.x, c.y); m[3] = make_float2(c.z, c.w);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(map + o));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(map + o) + 1);
+    m[0] = make_uint2(a.x, a.y); m[1] = make_uint2(a.z, a.w); m[2] = make_uint2(c.x, c.y); m[3] = make_uint2(c.z, c.w);
   } else {
 #pragma unroll
-    for (int k = 0; k < kRemapPx; k++) m[k] = (x0 + k < dw) ? __ldg(map + o + k) : make_float2(-8.f, -8.f);
+    for (int k = 0; k < kRemapPx; k++) m[k] = (x0 + k < dw) ? __ldg(map + o + k) : make_uint2(0x80008000u, 0u);
   }
   acc_t r[kRemapPx];
 #pragma unroll
   for (int k = 0; k < kRemapPx; k++) {
-    const int sx = cv_round(m[k].x * 32.0f), sy = cv_round(m[k].y * 32.0f);  // INTER_TAB_SIZE = 32
-    const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));  // saturate_cast<short>
-    const int fa = sx & 31, fb = sy & 31;
+    const int ix = (int)(short)(m[k].x & 0xffffu), iy = (int)m[k].x >> 16;
+    const int fa = (int)(m[k].y & 0xffu), fb = (int)(m[k].y >> 8);
     acc_t t0, t1, t2, t3;
     if ((unsigned)ix < (unsigned)(sw - 1) && (unsigned)iy < (unsigned)(sh - 1)) {
       const SrcT* p = s + (size_t)iy * sw + ix;
@@ -173,12 +184,24 @@ int camera_alloc_map(odo_ctx* c, odo_camera* cam, int w, int h) {
   if (cam->map && (cam->map_w != w || cam->map_h != h || cam->device != c->device)) {
     cudaStreamSynchronize(c->stream);
     cudaFree(cam->map);
+    cudaFree(cam->fix);
     cam->map = nullptr;
+    cam->fix = nullptr;
   }
   if (!cam->map) ODO_CUDA_OK(c, cudaMalloc(&cam->map, sizeof(float2) * (size_t)w * h));
+  if (!cam->fix) ODO_CUDA_OK(c, cudaMalloc(&cam->fix, sizeof(uint2) * (size_t)w * h));
   cam->map_w = w;
   cam->map_h = h;
   cam->device = c->device;
+  return 0;
+}
+
+int camera_fix_map(odo_ctx* c, odo_camera* cam) {
+  const int64_t n = (int64_t)cam->map_w * cam->map_h;
+  k_fix_map<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(cam->map, n, cam->fix);
+  c->launches++;
+  ODO_CUDA_OK(c, cudaGetLastError());
+  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -194,10 +217,10 @@ int launch_remap(odo_ctx* c, const odo_camera* cam, const void* src, int src_is_
   if (src_is_u8) {
     // cv::Scalar -> uchar: saturate_cast<uchar>(double) = round to nearest, clamp
     const double bv = border < 0 ? 0 : (border > 255 ? 255 : border);
-    k_remap<uint8_t><<<grid, block, 0, c->stream>>>((const uint8_t*)src, sstride, sw, sh, cam->map, dw, dh, dst_f, dst_8,
+    k_remap<uint8_t><<<grid, block, 0, c->stream>>>((const uint8_t*)src, sstride, sw, sh, cam->fix, dw, dh, dst_f, dst_8,
                                                     dstride, (int)__builtin_nearbyint(bv));
   } else {
-    k_remap<float><<<grid, block, 0, c->stream>>>((const float*)src, sstride, sw, sh, cam->map, dw, dh, dst_f, nullptr,
+    k_remap<float><<<grid, block, 0, c->stream>>>((const float*)src, sstride, sw, sh, cam->fix, dw, dh, dst_f, nullptr,
                                                   dstride, (float)border);
   }
   c->launches++;
@@ -228,6 +251,7 @@ void odo_camera_destroy(odo_camera* cam) {
   if (cam->map) {
     cudaSetDevice(cam->device);
     cudaFree(cam->map);
+    cudaFree(cam->fix);
   }
   delete cam;
 }
@@ -264,7 +288,7 @@ int odo_camera_configure(odo_ctx* c, odo_camera* cam, const double R[9], const d
   k_rectify_map<<<dim3((new_w + 255) / 256, new_h), 256, 0, c->stream>>>(k, new_w, new_h, cam->map);
   c->launches++;
   ODO_CUDA_OK(c, cudaGetLastError());
-  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (camera_fix_map(c, cam) != 0) return -1;
   cam->configured = true;
   return 0;
 }
@@ -278,7 +302,7 @@ int odo_camera_set_maps(odo_ctx* c, odo_camera* cam, const float* mapx, const fl
   std::vector<float2> m((size_t)w * h);
   for (size_t i = 0; i < m.size(); i++) m[i] = make_float2(mapx[i], mapy[i]);
   ODO_CUDA_OK(c, cudaMemcpyAsync(cam->map, m.data(), sizeof(float2) * m.size(), cudaMemcpyHostToDevice, c->stream));
-  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (camera_fix_map(c, cam) != 0) return -1;
   cam->configured = true;
   return 0;
 }
@@ -348,30 +372,46 @@ int odo_camera_undistort_rectify_dev(odo_ctx* c, const odo_camera* cam, const vo
   return rc;
 }
 
-int odo_camera_undistort_rectify(odo_ctx* c, const odo_camera* cam, const void* src, int src_type, int sw, int sh,
-                                 void* dst, int dst_type, double border_value) {
-  if (!c || !cam || !src || !dst || sw < 1 || sh < 1) return -1;
+int odo_camera_undistort_rectify_batch(odo_ctx* c, const odo_camera* cam, const void* const* srcs, int src_type, int sw,
+                                       int sh, void* const* dsts, int dst_type, int n, double border_value) {
+  if (!c || !cam || !srcs || !dsts || sw < 1 || sh < 1 || n < 1) return -1;
   if (!cam->configured) {
     c->err = "camera: ConfigureCamera has not run";
     return -1;
   }
-  if ((src_type != ODO_PIX_U8 && src_type != ODO_PIX_F32) || (dst_type != ODO_PIX_U8 && dst_type != ODO_PIX_F32)) return -1;
+  if ((src_type != ODO_PIX_U8 && src_type != ODO_PIX_F32) || (dst_type != ODO_PIX_U8 && dst_type != ODO_PIX_F32) ||
+      (src_type == ODO_PIX_F32 && dst_type == ODO_PIX_U8)) {
+    c->err = "camera: unsupported pixel type combination";
+    return -1;
+  }
   ODO_CUDA_OK(c, cudaSetDevice(c->device));
-  const size_t sb = (size_t)sw * sh * (src_type == ODO_PIX_U8 ? 1 : 4);
-  const size_t db = (size_t)cam->map_w * cam->map_h * (dst_type == ODO_PIX_U8 ? 1 : 4);
-  void *ds = nullptr, *dd = nullptr;
-  ODO_CUDA_OK(c, cudaMallocAsync(&ds, sb, c->stream));
-  ODO_CUDA_OK(c, cudaMallocAsync(&dd, db, c->stream));
+  const size_t spx = (size_t)sw * sh, dpx = (size_t)cam->map_w * cam->map_h;
+  const size_t sb = spx * (src_type == ODO_PIX_U8 ? 1 : 4), db = dpx * (dst_type == ODO_PIX_U8 ? 1 : 4);
+  // staging strides padded to 16 bytes so that every image of the batch keeps the vector alignment of the first
+  const size_t sstride_b = (sb + 15) / 16 * 16, dstride_b = (db + 15) / 16 * 16;
+  char *ds = nullptr, *dd = nullptr;
+  ODO_CUDA_OK(c, cudaMallocAsync(&ds, sstride_b * n, c->stream));
+  ODO_CUDA_OK(c, cudaMallocAsync(&dd, dstride_b * n, c->stream));
   int rc = 0;
-  if (cudaMemcpyAsync(ds, src, sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = -1;
+  for (int i = 0; i < n && rc == 0; i++)
+    if (!srcs[i] || !dsts[i] || cudaMemcpyAsync(ds + sstride_b * i, srcs[i], sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      rc = -1;
   if (rc == 0)
-    rc = odo_camera_undistort_rectify_dev(c, cam, ds, src_type, sw, sh, (int64_t)sw * sh, dd, dst_type,
-                                          (int64_t)cam->map_w * cam->map_h, 1, border_value);
-  if (rc == 0 && cudaMemcpyAsync(dst, dd, db, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = -1;
+    rc = odo_camera_undistort_rectify_dev(c, cam, ds, src_type, sw, sh, (int64_t)(sstride_b / (src_type == ODO_PIX_U8 ? 1 : 4)),
+                                          dd, dst_type, (int64_t)(dstride_b / (dst_type == ODO_PIX_U8 ? 1 : 4)), n, border_value);
+  for (int i = 0; i < n && rc == 0; i++)
+    if (cudaMemcpyAsync(dsts[i], dd + dstride_b * i, db, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = -1;
   cudaFreeAsync(ds, c->stream);
   cudaFreeAsync(dd, c->stream);
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = -1;
+  if (rc != 0 && c->err.empty()) c->err = "camera: batched undistort_rectify failed";
   return rc;
+}
+
+int odo_camera_undistort_rectify(odo_ctx* c, const odo_camera* cam, const void* src, int src_type, int sw, int sh,
+                                 void* dst, int dst_type, double border_value) {
+  if (!src || !dst) return -1;
+  return odo_camera_undistort_rectify_batch(c, cam, &src, src_type, sw, sh, &dst, dst_type, 1, border_value);
 }
 
 }  // extern "C"

@@ -18,4 +18,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_"
   python bench.py --seqs 64 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_$TAG.log 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_" -c 80 --csv --log-file $O/launches_${TAG}_4k.csv \
   python bench.py --workload 4k --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_launches_${TAG}_4k.log 2>&1
+timeout 300 python bench.py --workload rectify > $O/bench_${TAG}_rectify.json 2> $O/bench_${TAG}_rectify.err; tail -c 700 $O/bench_${TAG}_rectify.json
+timeout 300 python bench.py --workload rectify --impl reference --steps 3 > $O/bench_${TAG}_rectify_reference.json 2> $O/bench_${TAG}_rectify_reference.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_remap" -s 4 -c 2 -o $O/full_${TAG}_rectify -f \
+  python bench.py --workload rectify --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_${TAG}_rectify.log 2>&1
 ls -la $O
