@@ -110,16 +110,20 @@ __global__ void __launch_bounds__(128) k_remap(const SrcT* __restrict__ src, int
     const int fa = (int)(m[k].y & 0xffu), fb = (int)(m[k].y >> 8);
     acc_t t0, t1, t2, t3;
     if ((unsigned)ix < (unsigned)(sw - 1) && (unsigned)iy < (unsigned)(sh - 1)) {
-      const SrcT* p = s + (size_t)iy * sw + ix;
+      const SrcT* p = s + (iy * sw + ix);
       t0 = RemapTraits<SrcT>::load(p); t1 = RemapTraits<SrcT>::load(p + 1);
       t2 = RemapTraits<SrcT>::load(p + sw); t3 = RemapTraits<SrcT>::load(p + sw + 1);
+    } else if ((unsigned)(ix + 1) > (unsigned)sw || (unsigned)(iy + 1) > (unsigned)sh) {
+      // the whole 2x2 footprint is outside the raw frame (the black margin of a rectified image): no loads
+      t0 = t1 = t2 = t3 = cval;
     } else {  // BORDER_CONSTANT: texels outside the raw frame are the border value
       const bool x_in0 = (unsigned)ix < (unsigned)sw, x_in1 = (unsigned)(ix + 1) < (unsigned)sw;
       const bool y_in0 = (unsigned)iy < (unsigned)sh, y_in1 = (unsigned)(iy + 1) < (unsigned)sh;
-      t0 = (x_in0 && y_in0) ? RemapTraits<SrcT>::load(s + (size_t)iy * sw + ix) : cval;
-      t1 = (x_in1 && y_in0) ? RemapTraits<SrcT>::load(s + (size_t)iy * sw + ix + 1) : cval;
-      t2 = (x_in0 && y_in1) ? RemapTraits<SrcT>::load(s + (size_t)(iy + 1) * sw + ix) : cval;
-      t3 = (x_in1 && y_in1) ? RemapTraits<SrcT>::load(s + (size_t)(iy + 1) * sw + ix + 1) : cval;
+      const int off = iy * sw + ix;
+      t0 = (x_in0 && y_in0) ? RemapTraits<SrcT>::load(s + off) : cval;
+      t1 = (x_in1 && y_in0) ? RemapTraits<SrcT>::load(s + off + 1) : cval;
+      t2 = (x_in0 && y_in1) ? RemapTraits<SrcT>::load(s + off + sw) : cval;
+      t3 = (x_in1 && y_in1) ? RemapTraits<SrcT>::load(s + off + sw + 1) : cval;
     }
     if (sizeof(SrcT) == 1) {
       // 15-bit weights of remap's fixed-point path: 2^15 (1-a)(1-b) with a, b in 32nds is an exact integer

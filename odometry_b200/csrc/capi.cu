@@ -77,6 +77,14 @@ int odo_ctx_create(int device, void* cuda_stream, odo_ctx** out) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  {
+    // stream-ordered staging buffers (cudaMallocAsync in the host-buffer entry points) stay in the pool between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (cuda_stream) {
     c->stream = (cudaStream_t)cuda_stream;
     c->own_stream = false;
