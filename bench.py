@@ -822,14 +822,15 @@ def main():
     dom = max(critical, key=lambda k: stage_ms[k])
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")))
+        import glob
+        prof = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_traffic.json")))[-1]))  # newest capture
         if prof.get("sequences_per_launch") == St and dom in prof.get("stage_dram_bytes", {}):
             traffic = prof["stage_dram_bytes"][dom]
     except Exception:
         pass
     # a launch of the dominant kernel covers the St sequences of one tracker
     ach = alg_bytes[dom] * St / (stage_ms[dom] * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": {"disparity": "k_quantize + k_disparity<true,1280>"}.get(dom, dom), "stage": dom,
+    roof = {"bound": "hbm", "kernel": {"disparity": "k_disparity<true,1280,prune>"}.get(dom, dom), "stage": dom,
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
             "peak_source": peak_src, "launch_ms": stage_ms[dom],
             "algorithmic_bytes_per_launch": alg_bytes[dom] * St, "sequences_per_launch": St,
@@ -851,6 +852,8 @@ def main():
             peak_evals = sm * 4 * 16 * clk / 8.0              # 16 IMAD lanes per scheduler per clock, 8 IMAD per evaluation
             ach_evals = evals * St / (stage_ms[dom] * 1e-3)
             roof["issue_roofline"] = {"bound": "imad (fmaheavy pipe)", "unit": "candidate evaluations/s",
+                                      "note": "evaluations = the reference's (pixel, candidate) count; peak = 8 IMAD each at the "
+                                              "fmaheavy issue rate; the pruned scan rejects most candidates from a 2-IDP4A bound",
                                       "evaluations_per_frame": evals, "achieved": ach_evals, "peak": peak_evals,
                                       "frac": ach_evals / peak_evals}
         except Exception as e:  # the probe is informational
