@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "group_sync.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -398,23 +399,8 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
     if (QPATH) {
       constexpr int QP = PITCH;  // == q_pitch(W)
       const uint16_t* lq = d.qL + b * (int64_t)QP * H + (int64_t)y * QP;
-      int l2[PRUNE ? 1 : kDispP][8], El[kDispP], best[kDispP];
-      if (!PRUNE) {
-#pragma unroll
-        for (int i = 0; i < kDispP; i++) {
-          const uint16_t* c = lq + max(xs[i], 2);
-          const int t[8] = {c[2 * QP], c[QP - 1], c[2], c[0], c[-2], c[-QP + 1], c[-QP - 1], c[-2 * QP]};
-          int e = 0;
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            e += t[k] * t[k];
-            l2[PRUNE ? 0 : i][k] = 2 * t[k];
-          }
-          El[i] = e;
-          best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
-        }
-      }
-      if (PRUNE) {
+      int El[kDispP], best[kDispP];
+      if constexpr (PRUNE) {
         // The result only needs the minimum of the cost and, among equal costs, the smallest column (:382-386), so the
         // scan order is free: walk DOWN from the pixel.  The true match lies within the first chunks (disparities are
         // small against the row length); once it is known almost every other candidate can be rejected from a cheap
@@ -539,6 +525,20 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
         }
         if (base >= bnd) full_chunk(base, true);
       } else {
+        int l2[kDispP][8];
+#pragma unroll
+        for (int i = 0; i < kDispP; i++) {
+          const uint16_t* c = lq + max(xs[i], 2);
+          const int t[8] = {c[2 * QP], c[QP - 1], c[2], c[0], c[-2], c[-QP + 1], c[-QP - 1], c[-2 * QP]};
+          int e = 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            e += t[k] * t[k];
+            l2[i][k] = 2 * t[k];
+          }
+          El[i] = e;
+          best[i] = -0x7fffffff - 1;  // best = max of (2*cross - Er)  <=>  min of the SSD
+        }
         const uint16_t* q_c = reinterpret_cast<const uint16_t*>(s_rows) + 2 * PITCH + 2 + rx;
         const int* q_e = s_er + rx;
         // candidates below the smallest x of the group are candidates of every pixel: no range test
@@ -1042,6 +1042,35 @@ void depth_quant_reset(odo_ctx* c, const DepthWork& d, int batch) {
   if (d.exact) cudaMemsetAsync(d.exact, 0xff, sizeof(int) * batch, c->stream);
 }
 
+// One launch zero-fills every output plane of the depth stage (quirk Q6: val must be zero, disp / dep are zero-filled)
+// instead of one memset node per plane (the strided inverse-depth plane needed a 2-D memset): planes are given as
+// (base, bytes between sequences, bytes per sequence), written with 16-byte stores where the alignment allows.
+struct FillPlane {
+  char* base;
+  int64_t stride_b, width_b;
+  unsigned value;  // byte-replicated fill word
+};
+struct FillArgs {
+  FillPlane p[6];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_fill_planes(FillArgs a) {
+  const FillPlane pl = a.p[blockIdx.z];
+  char* base = pl.base + (int64_t)blockIdx.y * pl.stride_b;
+  const int64_t nb = pl.width_b;
+  const uint4 v = make_uint4(pl.value, pl.value, pl.value, pl.value);
+  const int64_t head = min(nb, (int64_t)((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15));
+  const int64_t nvec = (nb - head) >> 4;
+  uint4* vp = reinterpret_cast<uint4*>(base + head);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) vp[i] = v;
+  if (blockIdx.x == 0) {  // unaligned head and tail bytes
+    const int64_t tail0 = head + (nvec << 4);
+    for (int64_t i = threadIdx.x; i < head; i += blockDim.x) base[i] = (char)pl.value;
+    for (int64_t i = tail0 + threadIdx.x; i < nb; i += blockDim.x) base[i] = (char)pl.value;
+  }
+}
+
 void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                    const odo_depth_params& p, DepthWork& d, int batch, bool blur_left_done) {
   const size_t npx = (size_t)w * h;
@@ -1057,13 +1086,22 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
   }
   launch_blur3(c, R, stride, d.blurR, (int64_t)npx, w, h, batch, qr);
   d.q_ready = qe;
-  cudaMemsetAsync(d.val, 0, npx * batch, c->stream);
-  if (d.disp) cudaMemsetAsync(d.disp, 0, npx * batch * 4, c->stream);
-  if (d.dep_stride == (int64_t)npx) cudaMemsetAsync(d.dep, 0, npx * batch * 4, c->stream);
-  else cudaMemset2DAsync(d.dep, (size_t)d.dep_stride * 4, 0, npx * 4, batch, c->stream);
-  cudaMemsetAsync(d.stats, 0, sizeof(odo_depth_stats) * batch, c->stream);
-  if (d.match_x) cudaMemsetAsync(d.match_x, 0xff, npx * batch * 4, c->stream);
-  if (d.min_ssd) cudaMemsetAsync(d.min_ssd, 0, npx * batch * 4, c->stream);
+  {
+    FillArgs fa;
+    fa.n = 0;
+    auto add = [&](void* base, int64_t stride_b, int64_t width_b, unsigned value) {
+      if (base) fa.p[fa.n++] = FillPlane{(char*)base, stride_b, width_b, value};
+    };
+    add(d.val, (int64_t)npx, (int64_t)npx, 0u);
+    add(d.disp, (int64_t)npx * 4, (int64_t)npx * 4, 0u);
+    add(d.dep, d.dep_stride * 4, (int64_t)npx * 4, 0u);
+    add(d.stats, (int64_t)sizeof(odo_depth_stats), (int64_t)sizeof(odo_depth_stats), 0u);
+    add(d.match_x, (int64_t)npx * 4, (int64_t)npx * 4, 0xffffffffu);
+    add(d.min_ssd, (int64_t)npx * 4, (int64_t)npx * 4, 0u);
+    const int gx = (int)std::min<int64_t>(64, (int64_t)(npx * 4 / 16 + 255) / 256);
+    k_fill_planes<<<dim3(gx > 0 ? gx : 1, batch, fa.n), 256, 0, c->stream>>>(fa);
+    c->launches++;
+  }
   const int bn = ((w - 2 * p.boundary) / 32) * ((h - 2 * p.boundary) / 16);
   if (bn <= 32 * 28 && !std::getenv("ODO_SELECT_CTA"))
     k_select_warp<28><<<dim3(kGridBlocks / kSelWarpsPerCta, batch), 32 * kSelWarpsPerCta, 0, c->stream>>>(w, h, p, d);

@@ -164,3 +164,49 @@ def test_compute_depth_rejects_tiny_images(ctx):
     dp = capi.default_depth_params()
     rc, *_ = ctx.compute_depth(np.zeros((20, 30), np.float32), np.zeros((20, 30), np.float32), dp)
     assert rc == -1
+
+
+@pytest.mark.parametrize("case", ["scene", "repetitive", "flat_rows", "short_rows"])
+def test_pruned_scan_equals_plain_scan(ctx, pairs, case, monkeypatch):
+    """The integer path scans downwards and rejects chunks from a byte-domain lower bound; the plain
+    ascending scan stays available behind ODO_DISP_NOPRUNE.  Both must give the oracle's columns bit for bit, also where
+    pruning has nothing to hold on to: periodic texture (many equal costs: the FIRST minimum must win), rows whose
+    candidates all cost the same, and pixels so close to the left border that no full chunk exists."""
+    h, w = 376, 1241
+    op, dp = oracle.depth_params(), capi.default_depth_params()
+    rng = np.random.default_rng(11)
+    if case == "scene":
+        L, R = pairs[1]
+        _, bl, br, val = oracle.select_pixels(L, R, op)
+    else:
+        if case == "repetitive":
+            period = rng.integers(0, 256, 16).astype(np.float32)
+            R = np.tile(period, (h, w // 16 + 1))[:, :w].copy()
+            R += rng.integers(0, 2, (h, 1)).astype(np.float32)      # rows differ, columns repeat every 16
+            L = np.roll(R, 5, axis=1)
+        elif case == "flat_rows":
+            R = np.repeat(rng.integers(0, 256, (h, 1)).astype(np.float32), w, axis=1)
+            L = R.copy()
+        else:
+            R = rng.integers(0, 256, (h, w)).astype(np.float32)
+            L = np.roll(R, 3, axis=1)
+        bl, br = oracle.gaussian_blur3(L), oracle.gaussian_blur3(R)
+        val = np.zeros((h, w), np.uint8)
+        if case == "short_rows":
+            val[4:h - 4, 4:40:3] = 1                                 # candidates [4, x): fewer than one chunk
+            val[10, 4] = 1                                           # no candidate at all
+        else:
+            val[4:h - 4:3, 6:w - 4:37] = 1
+    orc, odisp, odep, omatch, _ = oracle.disparity_search(bl, br, val, op)
+    out = {}
+    for mode in ("prune", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("ODO_DISP_NOPRUNE", "1")
+        else:
+            monkeypatch.delenv("ODO_DISP_NOPRUNE", raising=False)
+        rc, disp, dep, match, _ = ctx.disparity_search(bl, br, val, dp, want_ssd=False)
+        assert rc == 0 and orc == 0
+        assert np.array_equal(match, omatch), f"{case}/{mode}"
+        assert bits_equal(disp, odisp) and bits_equal(dep, odep), f"{case}/{mode}"
+        out[mode] = match
+    assert np.array_equal(out["prune"], out["plain"])
