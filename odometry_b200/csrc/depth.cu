@@ -747,7 +747,11 @@ struct RefPass {
   const uint8_t* __restrict__ R8;
   float* dep;
   const int* __restrict__ sel_xy;
-  float4* __restrict__ st_a;   // {current, tmp, jtwj, b}
+  float2* __restrict__ st_a;   // {current, tmp}
+  float2* jb;                  // SHARED memory: {jtwj, b} of this thread's slots, [trip][thread] -- written at the end of a
+                               // visit and read at the start of the next one by the same thread, so it never has to leave the SM
+                               // (jb_shared == false: too many slots per CTA, a global array indexed by slot instead)
+  bool jb_shared;
   int2* __restrict__ st_b;     // {y << 16 | x, left intensity}
   int W, nslots, tid, nthreads;
   float txfx, gscale, wmax, huber_delta;
@@ -761,7 +765,8 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
   const bool take_tmp = pending == PEND_ACCEPT;
   const bool zero_cur = pending == PEND_REJECT && !accepted_once;
   const bool step = pending != PEND_NONE;
-  for (int s0 = rp.tid; s0 < rp.nslots; s0 += rp.nthreads * kRefUnroll) {
+  int trip = 0;
+  for (int s0 = rp.tid; s0 < rp.nslots; s0 += rp.nthreads * kRefUnroll, trip += kRefUnroll) {
     float4 sa[kRefUnroll];
     int2 sb[kRefUnroll];
 #pragma unroll
@@ -774,7 +779,9 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
           sb[u].x = rp.sel_xy[s];
         } else {
           sb[u] = rp.st_b[s];
-          sa[u] = rp.st_a[s];
+          const float2 ct = rp.st_a[s];
+          const float2 jb = rp.jb[rp.jb_shared ? (trip + u) * kRefThreads + threadIdx.x : s];
+          sa[u] = make_float4(ct.x, ct.y, jb.x, jb.y);
         }
       }
     }
@@ -832,7 +839,8 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
         njt = __fmul_rn(__fmul_rn(g, g), w_i);
         nbv = __fmul_rn(__fmul_rn(-g, w_i), r_i);
       }
-      rp.st_a[s] = make_float4(sa[u].x, sa[u].y, njt, nbv);
+      rp.st_a[s] = make_float2(sa[u].x, sa[u].y);
+      rp.jb[rp.jb_shared ? (trip + u) * kRefThreads + threadIdx.x : s] = make_float2(njt, nbv);
       if (FIRST) rp.st_b[s] = sb[u];
     }
   }
@@ -841,8 +849,9 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
 __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
                                                           int64_t stride, int W, int H, odo_depth_params p,
                                                           DepthWork d, double* partials, unsigned* barrier,
-                                                          int* abort_flag) {
+                                                          int* abort_flag, int jb_in_smem) {
   __shared__ RefShared sh;
+  extern __shared__ float2 s_jb[];  // refine_smem_bytes(): {jtwj, b} of every slot this CTA owns
   const int b = blockIdx.y;
   const int G = gridDim.x;
   GroupSync gs;
@@ -865,8 +874,11 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
   rp.nslots = d.cap;
   rp.sel_xy = d.sel_xy + (int64_t)b * rp.nslots;
-  rp.st_a = reinterpret_cast<float4*>(d.ref_state) + (int64_t)b * rp.nslots;
-  rp.st_b = reinterpret_cast<int2*>(d.ref_state + (int64_t)gridDim.y * 4 * rp.nslots) + (int64_t)b * rp.nslots;
+  rp.st_a = reinterpret_cast<float2*>(d.ref_state) + (int64_t)b * rp.nslots;
+  rp.st_b = reinterpret_cast<int2*>(d.ref_state + (int64_t)gridDim.y * 2 * rp.nslots) + (int64_t)b * rp.nslots;
+  rp.jb_shared = jb_in_smem != 0;
+  rp.jb = rp.jb_shared ? s_jb
+                       : reinterpret_cast<float2*>(d.ref_state + (int64_t)gridDim.y * 4 * rp.nslots) + (int64_t)b * rp.nslots;
   rp.W = W;
   rp.tid = blockIdx.x * kRefThreads + threadIdx.x;
   rp.nthreads = G * kRefThreads;
@@ -927,7 +939,7 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
     if (first) {
       cur = dep[o];
     } else {
-      const float4 a = rp.st_a[s];
+      const float2 a = rp.st_a[s];
       cur = a.x;
       const float wf = floorf(__fsub_rn((float)x, __fmul_rn(rp.txfx, a.y)));
       if (!(wf >= 2.0f && wf <= rp.wmax)) {
@@ -1157,15 +1169,45 @@ void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, Depth
 }
 
 // scratch for the refinement's group reduction lives behind the refinement state
+// dynamic shared memory of k_refine with G CTAs per sequence: {jtwj, b} of ceil(cap / (G * threads)) slots per thread,
+// rounded up to whole trips of the unrolled pass
+static size_t refine_smem_bytes(int cap, int G) {
+  const int per_thread = (cap + G * kRefThreads - 1) / (G * kRefThreads);
+  const int trips = (per_thread + kRefUnroll - 1) / kRefUnroll * kRefUnroll;
+  return sizeof(float2) * (size_t)trips * kRefThreads;
+}
+
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch) {
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  int G = (c->sm_count * per_sm) / (batch > 0 ? batch : 1);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
   const int gmax = (d.cap + kRefThreads - 1) / kRefThreads;  // one slot per thread
-  if (G > gmax) G = gmax;
-  if (G < 1) G = 1;
+  // G CTAs per sequence, all co-resident (group barrier).  Fewer CTAs per sequence mean more slots, hence more shared
+  // memory, per CTA, which can lower the occupancy again: settle from the register-limited value downwards.
+  int G = gmax;
+  size_t smem = refine_smem_bytes(d.cap, G);
+  for (int it = 0; it < 8; it++) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int g2 = (c->sm_count * per_sm) / (batch > 0 ? batch : 1);
+    if (g2 > gmax) g2 = gmax;
+    if (g2 < 1) g2 = 1;
+    if (g2 >= G) break;
+    G = g2;
+    smem = refine_smem_bytes(d.cap, G);
+  }
+  int jb_in_smem = 1;
+  if (smem > 200 * 1024) {  // very large batches: one CTA per sequence owns too many slots, the state stays in global memory
+    jb_in_smem = 0;
+    smem = 0;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, 0);
+    G = std::max(1, std::min(gmax, (c->sm_count * std::max(per_sm, 1)) / (batch > 0 ? batch : 1)));
+  }
   // partials / barrier / abort flag: carved from a small dedicated allocation owned by the context
   const size_t need = al(sizeof(double) * 2 * (size_t)G * 32 * batch) + al(sizeof(unsigned) * batch) + 256;
   if (c->scratch_bytes[15] < need) {
@@ -1196,10 +1238,10 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
     int64_t st = stride;
     odo_depth_params pp = p;
     void* args[] = {(void*)&L, (void*)&R, (void*)&st, (void*)&W, (void*)&H, (void*)&pp, (void*)&d,
-                    (void*)&partials, (void*)&barrier, (void*)&abort_flag};
-    e = cudaLaunchCooperativeKernel((const void*)k_refine, grid, block, args, 0, c->stream);
+                    (void*)&partials, (void*)&barrier, (void*)&abort_flag, (void*)&jb_in_smem};
+    e = cudaLaunchCooperativeKernel((const void*)k_refine, grid, block, args, smem, c->stream);
   } else {
-    k_refine<<<grid, block, 0, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag);
+    k_refine<<<grid, block, smem, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag, jb_in_smem);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) c->err = std::string("k_refine launch: ") + cudaGetErrorString(e);
