@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
   __syncthreads();
 
   const int ng = (n + kDispP - 1) / kDispP;
+  int n_ok = 0;  // accepted matches of this lane: one atomic per warp at the end instead of one per pixel on 64 hot counters
   for (int g0 = 0; g0 < ng; g0 += kDispWarps) {
     // snake order over the rounds: later groups have more candidates, alternate which warp gets them
     const int g = g0 + (((g0 / kDispWarps) & 1) ? (kDispWarps - 1 - wid) : wid);
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
           if (d.disp) d.disp[o] = disp;
           d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
           if (d.match_x) d.match_x[o] = w_rx;
-          atomicAdd(&d.stats[b].n_matched, 1);
+          n_ok++;
         }
       }
     } else {
@@ -666,12 +667,14 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
             if (d.disp) d.disp[o] = disp;
             d.dep[b * d.dep_stride + (int64_t)y * W + x] = __fdiv_rn(disp, __fmul_rn(p.fx, p.baseline));  // :394
             if (d.match_x) d.match_x[o] = brx[i];
-            atomicAdd(&d.stats[b].n_matched, 1);
+            n_ok++;
           }
         }
       }
     }
   }
+  n_ok = __reduce_add_sync(0xffffffffu, n_ok);
+  if (lane == 0 && n_ok) atomicAdd(&d.stats[b].n_matched, n_ok);
 }
 
 // ---- inverse-depth refinement ---------------------------------------------------------------------------

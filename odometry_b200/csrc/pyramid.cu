@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128, 8) k_blur3(const float* __restrict__ src,
     const int ym = min(y1, h - 1);
     // 8 rows per trip: the loads of the trip are independent of the rolling window and go out together (ncu: the
     // kernel waits on memory, long-scoreboard stalls, with 4 rows in flight per thread at 50 % occupancy)
-#pragma unroll 8
+#pragma unroll 16
     for (int y = y0; y < ym; y++) {
       r += w;
       const float t2 = blur_row(r, dm, dp);
