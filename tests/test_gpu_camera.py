@@ -163,3 +163,24 @@ def test_tracker_raw_ingest_equals_rectify_then_track(ctx, synth_data):
     ta.close(); tb.close()
     for c in cams:
         c.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 9])
+def test_batched_host_entry_and_image_groups(ctx, n):
+    """odo_camera_undistort_rectify_batch: n host frames in, n out with one launch; the kernel shares a table entry
+    between groups of four images, so batch sizes on both sides of a multiple of four are covered."""
+    cam = make_camera(ctx, SIDES[1])
+    mx, my = cam.maps()
+    rng = np.random.default_rng(40 + n)
+    src = rng.integers(0, 256, (n, 480, 640), dtype=np.uint8)
+    out_f = np.zeros((n, 480, 640), np.float32)
+    cam.undistort_rectify_batch_ptrs([src[i].ctypes.data for i in range(n)], True, 640, 480,
+                                     [out_f[i].ctypes.data for i in range(n)], False, border_value=7)
+    srcf = (src.astype(np.float32) + 0.25)
+    out_ff = np.zeros((n, 480, 640), np.float32)
+    cam.undistort_rectify_batch_ptrs([srcf[i].ctypes.data for i in range(n)], False, 640, 480,
+                                     [out_ff[i].ctypes.data for i in range(n)], False, border_value=7)
+    for i in range(n):
+        assert np.array_equal(out_f[i], oracle.remap_bilinear(src[i], mx, my, 7).astype(np.float32)), i
+        assert np.array_equal(out_ff[i].view(np.uint32), oracle.remap_bilinear(srcf[i], mx, my, 7).view(np.uint32)), i
+    cam.close()
