@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libodometry_dropin.so")
 DRIVER = os.path.join(HERE, "dropin_driver")
 SRCS = ["runtime.cpp", "image_pyramid.cpp", "image_processing_global.cpp", "depth_estimate.cpp", "lm_optimizer.cpp",
-        "camera.cpp"]
+        "camera.cpp", "stereo_rectify.cpp"]
 INCLUDES = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(HERE, "compat"), "-I", os.path.join(ROOT, "include")]
 CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off"]
 

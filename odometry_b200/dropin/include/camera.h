@@ -74,16 +74,23 @@ class CameraPyramid {
   odo_camera* cam_ = nullptr;  // owns the device-resident rmap_[0], rmap_[1]
 };
 
-// include/camera.h:120-131 of the reference.  The calibration-file reader is complete; SetUpStereoCameraSystem
-// needs cv::stereoRectify and is only functional in a build against the real OpenCV (calib3d): with the stand-in
-// headers it reads the file, creates both cameras and returns -1 (callers then run stereoRectify elsewhere and call
-// ConfigureCamera themselves).
+// include/camera.h:120-131 of the reference.  SetUpStereoCameraSystem runs cv::stereoRectify when the build has
+// OpenCV's calib3d and the restatement below otherwise (src/stereo_rectify.cpp, pinned to cv2 on the reference's
+// calibration file).
 GlobalStatus SetUpStereoCameraSystem(const std::string& stereo_file, int levels, std::shared_ptr<CameraPyramid>& cam_ptr_left,
                                      std::shared_ptr<CameraPyramid>& cam_ptr_right, cv::Rect& valid_region, double& baseline);
 void ReadStereoCalibrationFile(const std::string& stereo_file, cv::Mat& camera_intrin_left, cv::Mat& camera_intrin_right,
                                cv::Mat& dist_left, cv::Mat& dist_right, cv::Mat& rotate_left_right,
                                cv::Mat& translate_left_right, double& sensor_w_left, double& sensor_h_left,
                                double& sensor_w_right, double& sensor_h_right, int& resolution_w, int& resolution_h);
+
+namespace b200 {
+// cv::stereoRectify(K1, D1, K2, D2, Size(w, h), R, T, R1, R2, P1, P2, Q, CALIB_ZERO_DISPARITY, alpha, Size(w, h), &roi1,
+// &roi2) as SetUpStereoCameraSystem calls it (src/camera.cpp:139-141).  Row-major doubles: K, R 3x3, P 3x4; D = k1 k2 p1 p2.
+bool StereoRectify(const double K1[9], const double D1[4], const double K2[9], const double D2[4], int w, int h,
+                   const double R[9], const double T[3], double alpha, double R1[9], double R2[9], double P1[12],
+                   double P2[12], cv::Rect* roi1, cv::Rect* roi2);
+}  // namespace b200
 
 }  // namespace odometry
 #endif

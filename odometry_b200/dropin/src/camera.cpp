@@ -3,6 +3,7 @@
 #include <camera.h>
 #include <odo_b200_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -190,27 +191,49 @@ GlobalStatus SetUpStereoCameraSystem(const std::string& stereo_file, int levels,
   };
   cam_ptr_left = make(K0, D0, swl, shl);
   cam_ptr_right = make(K1, D1, swr, shr);
-#ifdef ODO_B200_HAVE_CALIB3D
   const cv::Size img_size(640, 480);  // src/camera.cpp:100
-  cv::Mat R1, R2, P1, P2, Q;
+  cv::Mat R1, R2, P1, P2;
   cv::Rect roi_l, roi_r;
+#ifdef ODO_B200_HAVE_CALIB3D
+  cv::Mat Q;
   cv::stereoRectify(K0, D0, K1, D1, img_size, R, T, R1, R2, P1, P2, Q, cv::CALIB_ZERO_DISPARITY, 1, img_size, &roi_l, &roi_r);
-  baseline = std::fabs(P2.at<double>(0, 3) / P2.at<double>(0, 0));
+#else
+  {
+    double k0[9], k1[9], d0[4], d1[4], r[9], t[3], r1[9], r2[9], p1[12], p2[12];
+    for (int i = 0; i < 9; i++) {
+      k0[i] = K0.at<double>(i / 3, i % 3);
+      k1[i] = K1.at<double>(i / 3, i % 3);
+      r[i] = R.at<double>(i / 3, i % 3);
+    }
+    for (int i = 0; i < 4; i++) {
+      d0[i] = D0.at<double>(0, i);
+      d1[i] = D1.at<double>(0, i);
+    }
+    for (int i = 0; i < 3; i++) t[i] = T.at<double>(i, 0);
+    if (!b200::StereoRectify(k0, d0, k1, d1, img_size.width, img_size.height, r, t, 1.0, r1, r2, p1, p2, &roi_l, &roi_r)) {
+      std::cout << "stereo rectification failed (zero baseline)" << std::endl;
+      return -1;
+    }
+    R1.create(3, 3, CV_64F); R2.create(3, 3, CV_64F); P1.create(3, 4, CV_64F); P2.create(3, 4, CV_64F);
+    for (int i = 0; i < 9; i++) {
+      R1.at<double>(i / 3, i % 3) = r1[i];
+      R2.at<double>(i / 3, i % 3) = r2[i];
+    }
+    for (int i = 0; i < 12; i++) {
+      P1.at<double>(i / 4, i % 4) = p1[i];
+      P2.at<double>(i / 4, i % 4) = p2[i];
+    }
+  }
+#endif
+  baseline = std::fabs(P2.at<double>(0, 3) / P2.at<double>(0, 0));  // :144
   cam_ptr_left->ConfigureCamera(R1, P1, img_size);
   cam_ptr_right->ConfigureCamera(R2, P2, img_size);
-  const int x0 = std::max(roi_l.x, roi_r.x), y0 = std::max(roi_l.y, roi_r.y);
+  const int x0 = std::max(roi_l.x, roi_r.x), y0 = std::max(roi_l.y, roi_r.y);  // :151-157
   const int x1 = std::min(roi_l.x + roi_l.width, roi_r.x + roi_r.width);
   const int y1 = std::min(roi_l.y + roi_l.height, roi_r.y + roi_r.height);
   valid_region = cv::Rect(x0, y0, x1 - x0, y1 - y0);
   std::cout << "stereo configuration done!" << std::endl;
   return 0;
-#else
-  (void)valid_region;
-  (void)baseline;
-  std::cout << "SetUpStereoCameraSystem: cv::stereoRectify needs the real OpenCV calib3d; this build uses the stand-in "
-               "headers. Run stereoRectify elsewhere and call ConfigureCamera on the two cameras." << std::endl;
-  return -1;
-#endif
 }
 
 }  // namespace odometry

@@ -15,6 +15,12 @@
 //       host I/O of run_odometry_kitti_offline.cpp:286-473 (no GPU): reads n KITTI poses, writes them back to
 //       <dir>/poses_out.txt with save_txt's formatting, the mean translation error against a copy shifted by
 //       (0.3, 0, 0.4) to <dir>/err.txt, and one synthetic keyframe (gray / mask / disparity PGM) + keyframe ids
+//   dropin_driver stereo <camchain.yaml> <out.bin>
+//       the rectification step of SetUpStereoCameraSystem without a GPU: ReadStereoCalibrationFile + the drop-in's
+//       stereoRectify; out.bin : R1[9] P1[12] R2[9] P2[12] doubles, roi1[4] roi2[4] int32
+//   dropin_driver setup <camchain.yaml> <out.bin>
+//       SetUpStereoCameraSystem itself (test_camera_setup.cpp:19): out.bin : baseline (double), valid region x y w h
+//       (int32), then per camera the level-0 fx fy cx cy (doubles)
 //   dropin_driver camera <camchain.yaml> <rect.f64> <raw.u8> <out.bin>
 //       what test_camera_setup.cpp does, with the stereoRectify results read from rect.f64 (R1[9] P1[12] R2[9]
 //       P2[12] doubles) because the image has no calib3d: ReadStereoCalibrationFile, two CameraPyramids,
@@ -321,7 +327,52 @@ static int Io(const char* poses_in, int n, const char* dir) {
   return 0;
 }
 
+static int Stereo(const char* yaml, const char* out_path) {
+  cv::Mat K[2] = {cv::Mat(3, 3, CV_64F), cv::Mat(3, 3, CV_64F)}, D[2] = {cv::Mat(1, 4, CV_64F), cv::Mat(1, 4, CV_64F)};
+  cv::Mat Rlr(3, 3, CV_64F), Tlr(3, 1, CV_64F);
+  double sw[2], sh[2];
+  int rw = 0, rh = 0;
+  odometry::ReadStereoCalibrationFile(yaml, K[0], K[1], D[0], D[1], Rlr, Tlr, sw[0], sh[0], sw[1], sh[1], rw, rh);
+  double R1[9], R2[9], P1[12], P2[12];
+  cv::Rect roi[2];
+  if (!odometry::b200::StereoRectify(K[0].ptr<double>(0), D[0].ptr<double>(0), K[1].ptr<double>(0), D[1].ptr<double>(0), 640, 480,
+                                    Rlr.ptr<double>(0), Tlr.ptr<double>(0), 1.0, R1, R2, P1, P2, &roi[0], &roi[1]))
+    return 3;
+  FILE* out = std::fopen(out_path, "wb");
+  if (!out) return 2;
+  std::fwrite(R1, sizeof(double), 9, out);
+  std::fwrite(P1, sizeof(double), 12, out);
+  std::fwrite(R2, sizeof(double), 9, out);
+  std::fwrite(P2, sizeof(double), 12, out);
+  for (int k = 0; k < 2; k++) {
+    const int v[4] = {roi[k].x, roi[k].y, roi[k].width, roi[k].height};
+    std::fwrite(v, sizeof(int), 4, out);
+  }
+  std::fclose(out);
+  return 0;
+}
+
+static int Setup(const char* yaml, const char* out_path) {
+  std::shared_ptr<odometry::CameraPyramid> left, right;
+  cv::Rect valid;
+  double baseline = 0;
+  if (odometry::SetUpStereoCameraSystem(yaml, 4, left, right, valid, baseline) != 0) return 3;
+  FILE* out = std::fopen(out_path, "wb");
+  if (!out) return 2;
+  std::fwrite(&baseline, sizeof(double), 1, out);
+  const int v[4] = {valid.x, valid.y, valid.width, valid.height};
+  std::fwrite(v, sizeof(int), 4, out);
+  for (auto& cam : {left, right}) {
+    const double k[4] = {cam->fx_double(0), cam->fy_double(0), cam->cx_double(0), cam->cy_double(0)};
+    std::fwrite(k, sizeof(double), 4, out);
+  }
+  std::fclose(out);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 4 && std::string(argv[1]) == "stereo") return Stereo(argv[2], argv[3]);
+  if (argc >= 4 && std::string(argv[1]) == "setup") return Setup(argv[2], argv[3]);
   if (argc >= 5 && std::string(argv[1]) == "io") return Io(argv[2], std::atoi(argv[3]), argv[4]);
   if (argc >= 6 && std::string(argv[1]) == "camera") return Camera(argv[2], argv[3], argv[4], argv[5]);
   if (argc >= 7 && std::string(argv[1]) == "track")

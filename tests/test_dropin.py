@@ -268,3 +268,54 @@ def test_dropin_kitti_io_round_trip(dropin, tmp_path):
     dep = (np.float32(0.01) * (x + 1).astype(np.float32) * (y + 1).astype(np.float32)).astype(np.float32)
     assert np.array_equal(d, np.where(m != 0, (np.float32(386.1448) * dep).astype(np.uint16), 0))
     assert open(tmp_path / "keyframe_id.txt").read().split() == ["0", "7", "19"]
+
+
+def test_dropin_stereo_rectify_matches_cv2_golden(dropin, tmp_path):
+    """The drop-in's restatement of cv::stereoRectify (used by SetUpStereoCameraSystem when the build has no calib3d) on the
+    reference's calibration file against cv2 4.13.0 (tests/golden/cv2_camera.npz) -- host arithmetic, no GPU."""
+    _, driver = dropin
+    _write_camchain(tmp_path / "camchain.yaml")
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cv2_camera.npz"))
+    r = subprocess.run([driver, "stereo", str(tmp_path / "camchain.yaml"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(tmp_path / "o.bin", "rb").read()
+    d = np.frombuffer(raw, np.float64, 42)
+    rois = np.frombuffer(raw, np.int32, 8, 42 * 8)
+    R1, P1, R2, P2 = d[:9].reshape(3, 3), d[9:21].reshape(3, 4), d[21:30].reshape(3, 3), d[30:42].reshape(3, 4)
+    assert np.abs(R1 - G["R1"]).max() < 1e-14 and np.abs(R2 - G["R2"]).max() < 1e-14
+    assert np.abs(P1 - G["P1"]).max() < 1e-6 and np.abs(P2 - G["P2"]).max() < 1e-6
+    assert np.array_equal(P1[:, 2], G["P1"][:, 2]) and np.array_equal(P2[:, 2], G["P2"][:, 2])   # principal points: exact
+    assert tuple(rois[:4]) == tuple(G["roi1"]) and tuple(rois[4:]) == tuple(G["roi2"])
+    # the rectified images do not depend on the 1e-9 relative difference of the focal length: same fixed-point tables
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import camera_patterns as cp
+    for K, D, R, P, Rg, Pg in (("K0", "D0", R1, P1, "R1", "P1"), ("K1", "D1", R2, P2, "R2", "P2")):
+        mx, my = oracle.init_undistort_rectify_map(G[K], G[D], R, P, cp.RAW_SIZE)
+        gx, gy = oracle.init_undistort_rectify_map(G[K], G[D], G[Rg], G[Pg], cp.RAW_SIZE)
+        fx_ = lambda m: np.rint(m * np.float32(32)).astype(np.int64)
+        assert (fx_(mx) != fx_(gx)).mean() < 1e-4 and (fx_(my) != fx_(gy)).mean() < 1e-4
+        assert np.abs(mx - gx).max() < 1e-4 and np.abs(my - gy).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_dropin_set_up_stereo_camera_system(dropin, tmp_path):
+    """SetUpStereoCameraSystem end to end (test_camera_setup.cpp:19): baseline, valid region, rectified intrinsics."""
+    _, driver = dropin
+    _write_camchain(tmp_path / "camchain.yaml")
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cv2_camera.npz"))
+    r = subprocess.run([driver, "setup", str(tmp_path / "camchain.yaml"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "stereo configuration done!" in r.stdout
+    raw = open(tmp_path / "o.bin", "rb").read()
+    baseline = np.frombuffer(raw, np.float64, 1)[0]
+    valid = tuple(np.frombuffer(raw, np.int32, 4, 8))
+    k = np.frombuffer(raw, np.float64, 8, 24).reshape(2, 4)
+    P2 = G["P2"]
+    assert baseline == pytest.approx(abs(P2[0, 3] / P2[0, 0]), rel=1e-9)
+    r1, r2 = G["roi1"], G["roi2"]
+    x0, y0 = max(r1[0], r2[0]), max(r1[1], r2[1])
+    x1, y1 = min(r1[0] + r1[2], r2[0] + r2[2]), min(r1[1] + r1[3], r2[1] + r2[3])
+    assert valid == (x0, y0, x1 - x0, y1 - y0)                       # src/camera.cpp:151-157
+    for i, P in enumerate((G["P1"], G["P2"])):
+        assert k[i] == pytest.approx([P[0, 0], P[1, 1], P[0, 2], P[1, 2]], rel=1e-8)
