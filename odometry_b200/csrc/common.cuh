@@ -88,8 +88,11 @@ void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int
                   QuantOut q = QuantOut());
 void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
                     int dw, int dh, int batch);
+// part: the tracker builds level 0 (needed by the depth stage) on its main stream and levels 1.. (needed only by the LM
+// solve) on the LM stream
+enum { PYR_ALL = 0, PYR_LEVEL0 = 1, PYR_UPPER_LEVELS = 2 };
 void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
-                          const PyrGeom& g, int smooth, int batch, QuantOut q0 = QuantOut());
+                          const PyrGeom& g, int smooth, int batch, QuantOut q0 = QuantOut(), int part = PYR_ALL);
 void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,
                           const PyrGeom& g, int smooth, int batch);
 

@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(128, 8) k_blur3(const float* __restrict__ src,
     float t1 = blur_row(r, dm, dp);
     // rows whose successor is inside the image: the source pointer just advances
     const int ym = min(y1, h - 1);
-    // 8 rows per trip: the loads of the trip are independent of the rolling window and go out together (ncu: the
-    // kernel waits on memory, long-scoreboard stalls, with 4 rows in flight per thread at 50 % occupancy)
+    // the whole strip unrolled: its loads are independent of the rolling window and go out together (ncu: with 4 rows
+    // in flight per thread at 50 % occupancy the kernel waited on memory, long-scoreboard stalls, at 2.2 TB/s)
 #pragma unroll 16
     for (int y = y0; y < ym; y++) {
       r += w;
@@ -266,13 +266,16 @@ void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int s
 }
 
 void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
-                          const PyrGeom& g, int smooth, int batch, QuantOut q0) {
+                          const PyrGeom& g, int smooth, int batch, QuantOut q0, int part) {
   const int64_t n0 = (int64_t)g.w[0] * g.h[0];
-  if (smooth) {
-    launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch, q0);
-  } else {
-    launch_copy_batched(c, img, istride, pyr, pstride, n0, batch);
+  if (part != PYR_UPPER_LEVELS) {
+    if (smooth) {
+      launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch, q0);
+    } else {
+      launch_copy_batched(c, img, istride, pyr, pstride, n0, batch);
+    }
   }
+  if (part == PYR_LEVEL0) return;
   if (g.levels > 1)  // level 1 from the RAW input (quirk Q5)
     launch_pyrdown(c, img, istride, g.w[0], g.h[0], pyr + g.off[1], pstride, g.w[1], g.h[1], batch);
   for (int l = 2; l < g.levels; l++)

@@ -234,7 +234,10 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
   // level 0 doubles as the blurred left image of the depth stage: emit its u16 copy for the integer line search
   depth_quant_reset(c, t->dw, n);
-  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, depth_quant_left(t->dw, t->dp, t->w, t->h));
+  // level 0 here; levels 1.. are only read by the LM solve (and, after the join, by the point-list build): on frames
+  // that track they are built on the LM stream, off the critical path of the depth pipeline
+  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, depth_quant_left(t->dw, t->dp, t->w, t->h),
+                       first ? PYR_ALL : PYR_LEVEL0);
   cudaEventRecord(ev[1], c->stream);
   t->lm_ran[slot] = !first;
   if (!first) {
@@ -244,6 +247,7 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
     cudaStreamWaitEvent(t->lm_stream, t->ev_fork, 0);
     c->stream = t->lm_stream;
     cudaEventRecord(t->ev_lm[slot][0], t->lm_stream);
+    launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, QuantOut(), PYR_UPPER_LEVELS);
     const int rc = launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n,
                                    t->G_lm, -1);
     if (rc == 0) {
@@ -266,10 +270,13 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   if (R8) cudaMemsetAsync(t->dw.raw_exact, 0xff, sizeof(int) * n, c->stream);  // u8 frames are exact by construction
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(ev[5], c->stream);
-  cudaEventRecord(t->ev_consumed[slot], c->stream);  // nothing after this point reads the input frame
+  if (first) cudaEventRecord(t->ev_consumed[slot], c->stream);  // nothing after this point reads the input frame
   // DepthPyramid(levels, dep, false) (:252) is a pure subsampling of the refined map: the point lists below read
   // it through level 0, nothing else in the loop looks at levels 1.., so it is not materialised
-  if (!first) cudaStreamWaitEvent(c->stream, t->ev_lm_done, 0);  // join: the keyframe rule needs the pose
+  if (!first) {
+    cudaStreamWaitEvent(c->stream, t->ev_lm_done, 0);  // join: the keyframe rule needs the pose
+    cudaEventRecord(t->ev_consumed[slot], c->stream);  // the LM stream read the raw frame too (pyramid level 1, quirk Q5)
+  }
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
   c->launches++;
   // keyframe promotion (:258-265): the only thing Solve needs from a keyframe are its point lists, built
