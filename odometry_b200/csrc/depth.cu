@@ -1204,7 +1204,8 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
     smem = refine_smem_bytes(d.cap, G);
   }
   int jb_in_smem = 1;
-  if (smem > 200 * 1024) {  // very large batches: one CTA per sequence owns too many slots, the state stays in global memory
+  if (smem > 200 * 1024 || std::getenv("ODO_REFINE_GLOBAL_STATE")) {  // very large batches: one CTA per sequence owns too many
+                                                                       // slots, the state stays in global memory (env: test hook)
     jb_in_smem = 0;
     smem = 0;
     int per_sm = 1;

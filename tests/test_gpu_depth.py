@@ -210,3 +210,17 @@ def test_pruned_scan_equals_plain_scan(ctx, pairs, case, monkeypatch):
         assert bits_equal(disp, odisp) and bits_equal(dep, odep), f"{case}/{mode}"
         out[mode] = match
     assert np.array_equal(out["prune"], out["plain"])
+
+
+def test_refinement_state_in_shared_or_global_memory(ctx, pairs, monkeypatch):
+    """k_refine keeps {jtwj, b} of its slots in shared memory and falls back to a global array for very large batches;
+    both placements must give the same bits (the fallback is forced here through its test switch)."""
+    L, R = pairs[0]
+    dp = capi.default_depth_params()
+    monkeypatch.delenv("ODO_REFINE_GLOBAL_STATE", raising=False)
+    a = ctx.compute_depth(L, R, dp)
+    monkeypatch.setenv("ODO_REFINE_GLOBAL_STATE", "1")
+    b = ctx.compute_depth(L, R, dp)
+    assert a[0] == b[0] == 0
+    assert np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2]) and bits_equal(a[3], b[3])
+    assert (a[4].iters, a[4].n_valid, a[4].cost) == (b[4].iters, b[4].n_valid, b[4].cost)
