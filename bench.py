@@ -33,10 +33,23 @@ sys.path.insert(0, ROOT)
 
 W, H, LEVELS = 1241, 376, 4
 METRIC = "KITTI-shape tracking frames/s (pyramid + disparity/depth + LM align per frame)"
+def host_cpu():
+    """model name and logical core count of the host the CPU arm runs on (reported with the baseline)"""
+    model = "unknown CPU"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return f"{model}, {os.cpu_count()} logical cores"
+
+
 CPU_KIND_NOTE = {
     "reference": "the reference's own classes (oracle/_ref: its hot-path sources compiled unmodified against stand-in "
-                 "Eigen/OpenCV/Sophus headers, the loop of run_odometry_kitti_offline.cpp:95-271 around them)",
-    "port": "oracle port of the reference (oracle/_ref not present)",
+                 "Eigen/OpenCV/Sophus headers, the loop of run_odometry_kitti_offline.cpp:95-271 around them); host: " + host_cpu(),
+    "port": "oracle port of the reference (oracle/_ref not present); host: " + host_cpu(),
 }
 
 
@@ -526,7 +539,8 @@ def run_reference_rectify(args, rank):
             "dtype": "u8", "data": "synthetic", "config": config_rect(args, n),
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                              "sample": f"{n} pairs per step, one thread per logical core; the oracle's restatement of cv::remap "
-                                       "(the reference calls OpenCV here; oracle/camera.cpp is pinned bit-exactly to cv2 4.13.0)"},
+                                       "(the reference calls OpenCV here; oracle/camera.cpp is pinned bit-exactly to cv2 4.13.0); "
+                                       "host: " + host_cpu()},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -626,7 +640,7 @@ def run_rectify(args, rank, local_rank, world):
         cpu_rectify_pairs_per_s(raw_np[:2], maps, 1)
         v = cpu_rectify_pairs_per_s(raw_np[:n], maps, 1)
         cpu = {"value": v, "unit": "pairs/s", "cores": 1, "kind": "port",
-               "sample": f"{n} pairs, 1 thread; the oracle's restatement of cv::remap (pinned bit-exactly to cv2 4.13.0)"}
+               "sample": f"{n} pairs, 1 thread; the oracle's restatement of cv::remap (pinned bit-exactly to cv2 4.13.0); host: " + host_cpu()}
         ctx.sync()
         chk = out[0, 0].cpu().numpy()
         ref0 = oracle.remap_bilinear(raws[(Wm + K - 1) % nbuf][0, 0].cpu().numpy(), maps[0][0], maps[0][1], 0).astype(np.float32)
