@@ -18,6 +18,8 @@
 //   dropin_driver stereo <camchain.yaml> <out.bin>
 //       the rectification step of SetUpStereoCameraSystem without a GPU: ReadStereoCalibrationFile + the drop-in's
 //       stereoRectify; out.bin : R1[9] P1[12] R2[9] P2[12] doubles, roi1[4] roi2[4] int32
+//   dropin_driver stereo_raw <in.f64> <out.bin>
+//       the same step on a calibration given as doubles: K0[9] D0[4] K1[9] D1[4] R[9] T[3]; same out.bin
 //   dropin_driver setup <camchain.yaml> <out.bin>
 //       SetUpStereoCameraSystem itself (test_camera_setup.cpp:19): out.bin : baseline (double), valid region x y w h
 //       (int32), then per camera the level-0 fx fy cx cy (doubles)
@@ -352,6 +354,27 @@ static int Stereo(const char* yaml, const char* out_path) {
   return 0;
 }
 
+static int StereoRaw(const char* in_path, const char* out_path) {
+  const std::vector<unsigned char> in = ReadAll(in_path);
+  if (in.size() != 38 * sizeof(double)) return 2;
+  const double* v = reinterpret_cast<const double*>(in.data());
+  double R1[9], R2[9], P1[12], P2[12];
+  cv::Rect roi[2];
+  if (!odometry::b200::StereoRectify(v, v + 9, v + 13, v + 22, 640, 480, v + 26, v + 35, 1.0, R1, R2, P1, P2, &roi[0], &roi[1])) return 3;
+  FILE* out = std::fopen(out_path, "wb");
+  if (!out) return 2;
+  std::fwrite(R1, sizeof(double), 9, out);
+  std::fwrite(P1, sizeof(double), 12, out);
+  std::fwrite(R2, sizeof(double), 9, out);
+  std::fwrite(P2, sizeof(double), 12, out);
+  for (int k = 0; k < 2; k++) {
+    const int r[4] = {roi[k].x, roi[k].y, roi[k].width, roi[k].height};
+    std::fwrite(r, sizeof(int), 4, out);
+  }
+  std::fclose(out);
+  return 0;
+}
+
 static int Setup(const char* yaml, const char* out_path) {
   std::shared_ptr<odometry::CameraPyramid> left, right;
   cv::Rect valid;
@@ -372,6 +395,7 @@ static int Setup(const char* yaml, const char* out_path) {
 
 int main(int argc, char** argv) {
   if (argc >= 4 && std::string(argv[1]) == "stereo") return Stereo(argv[2], argv[3]);
+  if (argc >= 4 && std::string(argv[1]) == "stereo_raw") return StereoRaw(argv[2], argv[3]);
   if (argc >= 4 && std::string(argv[1]) == "setup") return Setup(argv[2], argv[3]);
   if (argc >= 5 && std::string(argv[1]) == "io") return Io(argv[2], std::atoi(argv[3]), argv[4]);
   if (argc >= 6 && std::string(argv[1]) == "camera") return Camera(argv[2], argv[3], argv[4], argv[5]);

@@ -69,6 +69,22 @@ def camera():
         d = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=9)
         out[f"stress/remap_{tag}_sha"] = digest(d)
         out[f"stress/remap_{tag}_rows"] = d[::16].copy()
+    # more stereo geometries for the drop-in's stereoRectify restatement (dropin/src/stereo_rectify.cpp): a strongly
+    # converging pair, a pair with the right camera on the other side, and a vertical pair (baseline along y)
+    rng = np.random.default_rng(20190124)
+    for i, (rvec, tvec) in enumerate([((0.03, -0.08, 0.02), (-0.12, 0.004, 0.01)), ((-0.01, 0.05, -0.03), (0.09, -0.002, -0.004)),
+                                      ((0.02, 0.01, -0.015), (0.003, -0.11, 0.006))]):
+        Ka = kmat([420 + 20 * rng.random(), 425 + 20 * rng.random(), 320 + 30 * rng.random(), 240 + 20 * rng.random()])
+        Kb = kmat([420 + 20 * rng.random(), 425 + 20 * rng.random(), 320 + 30 * rng.random(), 240 + 20 * rng.random()])
+        Da = np.array([-0.3 + 0.1 * rng.random(), 0.08 + 0.04 * rng.random(), 1e-3 * (rng.random() - 0.5), 1e-3 * (rng.random() - 0.5)])
+        Db = np.array([-0.3 + 0.1 * rng.random(), 0.08 + 0.04 * rng.random(), 1e-3 * (rng.random() - 0.5), 1e-3 * (rng.random() - 0.5)])
+        Rm = cv2.Rodrigues(np.array(rvec, np.float64))[0]
+        tv = np.array(tvec, np.float64).reshape(3, 1)
+        r1, r2, p1, p2, _, ro1, ro2 = cv2.stereoRectify(Ka, Da, Kb, Db, RAW_SIZE, Rm, tv, flags=cv2.CALIB_ZERO_DISPARITY, alpha=1,
+                                                       newImageSize=RAW_SIZE)
+        out.update({f"stereo{i}/K0": Ka, f"stereo{i}/K1": Kb, f"stereo{i}/D0": Da, f"stereo{i}/D1": Db, f"stereo{i}/R": Rm,
+                    f"stereo{i}/t": tv, f"stereo{i}/R1": r1, f"stereo{i}/R2": r2, f"stereo{i}/P1": p1, f"stereo{i}/P2": p2,
+                    f"stereo{i}/roi1": np.array(ro1), f"stereo{i}/roi2": np.array(ro2)})
     np.savez_compressed(os.path.join(HERE, "cv2_camera.npz"), **out)
     print("wrote", os.path.join(HERE, "cv2_camera.npz"))
 

@@ -298,6 +298,27 @@ def test_dropin_stereo_rectify_matches_cv2_golden(dropin, tmp_path):
         assert np.abs(mx - gx).max() < 1e-4 and np.abs(my - gy).max() < 1e-4
 
 
+@pytest.mark.parametrize("case", [0, 1, 2], ids=["converging", "right_camera_on_the_left", "vertical_pair"])
+def test_dropin_stereo_rectify_other_geometries(dropin, tmp_path, case):
+    """More stereo geometries against cv2 (strong convergence, negative baseline, baseline along y)."""
+    _, driver = dropin
+    G = np.load(os.path.join(ROOT, "tests", "golden", "cv2_camera.npz"))
+    g = lambda k: G[f"stereo{case}/{k}"]
+    np.concatenate([g("K0").ravel(), g("D0").ravel(), g("K1").ravel(), g("D1").ravel(), g("R").ravel(), g("t").ravel()]).astype(
+        np.float64).tofile(tmp_path / "in.f64")
+    r = subprocess.run([driver, "stereo_raw", str(tmp_path / "in.f64"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(tmp_path / "o.bin", "rb").read()
+    d = np.frombuffer(raw, np.float64, 42)
+    rois = np.frombuffer(raw, np.int32, 8, 42 * 8)
+    R1, P1, R2, P2 = d[:9].reshape(3, 3), d[9:21].reshape(3, 4), d[21:30].reshape(3, 3), d[30:42].reshape(3, 4)
+    assert np.abs(R1 - g("R1")).max() < 1e-13 and np.abs(R2 - g("R2")).max() < 1e-13
+    # OpenCV forms the scale of the new focal length from rectangles it keeps in float: agreement is to float precision
+    assert np.allclose(P1, g("P1"), rtol=5e-7, atol=1e-9) and np.allclose(P2, g("P2"), rtol=5e-7, atol=1e-9)
+    assert np.array_equal(P1[:, 2], g("P1")[:, 2]) and np.array_equal(P2[:, 2], g("P2")[:, 2])   # principal points: exact
+    assert np.abs(rois[:4] - g("roi1")).max() <= 1 and np.abs(rois[4:] - g("roi2")).max() <= 1
+
+
 @pytest.mark.gpu
 def test_dropin_set_up_stereo_camera_system(dropin, tmp_path):
     """SetUpStereoCameraSystem end to end (test_camera_setup.cpp:19): baseline, valid region, rectified intrinsics."""
