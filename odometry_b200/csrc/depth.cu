@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(32 * kSelWarpsPerCta) k_select_warp(int W, int
   // block_grad[n / 2] after std::nth_element (:324): magnitudes are >= +0, so bit patterns order like values
   const int k = n / 2;
   unsigned ans = 0u;
+  int below_lo = 0, below_hi = n;  // #{v < ans} and #{v < ans + 2^(bit+1)}: the k-th smallest lies in between
 #pragma unroll 1
   for (int bit = 30; bit >= 0; bit--) {
     const unsigned cand = ans | (1u << bit);
@@ -181,7 +182,21 @@ __global__ void __launch_bounds__(32 * kSelWarpsPerCta) k_select_warp(int W, int
 #pragma unroll
     for (int j = 0; j < NPL; j++) cnt += (v[j] < cand) ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (cnt <= k) ans = cand;
+    if (cnt <= k) {
+      ans = cand;
+      below_lo = cnt;
+    } else {
+      below_hi = cnt;
+    }
+    if (below_hi - below_lo == 1) {
+      // one value left in [ans, ans + 2^bit): it IS the k-th smallest, the remaining bits need no more counting rounds
+      const unsigned hi = ans + (1u << bit);
+      unsigned f = 0u;
+#pragma unroll
+      for (int j = 0; j < NPL; j++) f = (v[j] >= ans && v[j] < hi) ? v[j] : f;
+      ans = __reduce_max_sync(0xffffffffu, f);
+      break;
+    }
   }
   const float block_th = __fadd_rn(__uint_as_float(ans), p.grad_th);  // :325
   // first <= 80 pixels with mag > th in raster order, :327-341
