@@ -35,30 +35,32 @@ class CameraPyramid {
   GlobalStatus UndistortRectify(const cv::Mat& src_raw, cv::Mat& dst, int interpolation = cv::INTER_LINEAR,
                                 int borderMode = cv::BORDER_CONSTANT, const cv::Scalar& borderValue = cv::Scalar());
 
-  float fx_float(int level) { return float(intrinsic_[level].at<double>(0, 0)); }
-  float fy_float(int level) { return float(intrinsic_[level].at<double>(1, 1)); }
-  float f_theta_float(int level) { return float(intrinsic_[level].at<double>(0, 1)); }
-  float cx_float(int level) { return float(intrinsic_[level].at<double>(0, 2)); }
-  float cy_float(int level) { return float(intrinsic_[level].at<double>(1, 2)); }
-  float f_meters_float(int level) { return float(intrinsic_[level].at<double>(0, 0) / pixels_per_mm_x_); }
-  double fx_double(int level) { return intrinsic_[level].at<double>(0, 0); }
-  double fy_double(int level) { return intrinsic_[level].at<double>(1, 1); }
-  double f_theta_double(int level) { return intrinsic_[level].at<double>(0, 1); }
-  double cx_double(int level) { return intrinsic_[level].at<double>(0, 2); }
-  double cy_double(int level) { return intrinsic_[level].at<double>(1, 2); }
-  double f_meters_double(int level) { return intrinsic_[level].at<double>(0, 0) / pixels_per_mm_x_; }
+  // Rectified intrinsics of a pyramid level in pixels (include/camera.h:68-82 of the reference) and the raw hardware
+  // figures (:87-103), each as float and as double.  K_(l, r, c) is element (r, c) of level l's 3x3 matrix.
+  float fx_float(int level) { return float(K_(level, 0, 0)); }
+  float fy_float(int level) { return float(K_(level, 1, 1)); }
+  float f_theta_float(int level) { return float(K_(level, 0, 1)); }
+  float cx_float(int level) { return float(K_(level, 0, 2)); }
+  float cy_float(int level) { return float(K_(level, 1, 2)); }
+  float f_meters_float(int level) { return float(f_meters_double(level)); }
+  double fx_double(int level) { return K_(level, 0, 0); }
+  double fy_double(int level) { return K_(level, 1, 1); }
+  double f_theta_double(int level) { return K_(level, 0, 1); }
+  double cx_double(int level) { return K_(level, 0, 2); }
+  double cy_double(int level) { return K_(level, 1, 2); }
+  double f_meters_double(int level) { return K_(level, 0, 0) / pixels_per_mm_x_; }
   const cv::Mat& get_intrinsic_rectified(int level) { return intrinsic_[level]; }
 
   double sensor_w_double() { return sensor_width_; }
   double sensor_h_double() { return sensor_height_; }
   double pixels_per_mm_x_double() { return pixels_per_mm_x_; }
   double pixels_per_mm_y_double() { return pixels_per_mm_y_; }
+  float sensor_w_float() { return float(sensor_w_double()); }
+  float sensor_h_float() { return float(sensor_h_double()); }
+  float pixels_per_mm_x_float() { return float(pixels_per_mm_x_double()); }
+  float pixels_per_mm_y_float() { return float(pixels_per_mm_y_double()); }
   int resolution_raw_w() { return resolution_width_; }
   int resolution_raw_h() { return resolution_height_; }
-  float sensor_w_float() { return float(sensor_width_); }
-  float sensor_h_float() { return float(sensor_height_); }
-  float pixels_per_mm_x_float() { return float(pixels_per_mm_x_); }
-  float pixels_per_mm_y_float() { return float(pixels_per_mm_y_); }
   const cv::Mat& get_intrinsic_raw() { return intrinsic_raw_; }
   const cv::Mat& get_distortion_coeff() { return distortion_param_; }
 
@@ -66,6 +68,7 @@ class CameraPyramid {
   odo_camera* handle() const { return cam_; }
 
  private:
+  double K_(int level, int r, int c) const { return intrinsic_[level].at<double>(r, c); }
   cv::Mat intrinsic_raw_, distortion_param_;
   int resolution_width_, resolution_height_;
   double sensor_width_, sensor_height_, pixels_per_mm_x_, pixels_per_mm_y_;

@@ -20,15 +20,15 @@ class ImagePyramid {
   EIGEN_MAKE_ALIGNED_OPERATOR_NEW
   ImagePyramid() = delete;
   // smooth: blur level 0 with the 3x3 Gaussian (level 1 is always built from the raw input)
-  ImagePyramid(int num_levels, const cv::Mat& in_img, bool smooth);
+  ImagePyramid(int levels, const cv::Mat& image, bool smooth_level0);
   ImagePyramid& operator=(const ImagePyramid&) = delete;
 
-  int GetNumberLevels() const { return num_levels_; }
-  const cv::Mat& GetPyramidImage(int level_idx) const;
+  int GetNumberLevels() const { return level_count_; }
+  const cv::Mat& GetPyramidImage(int level) const;
 
  private:
   friend class LevenbergMarquardtOptimizer;
-  int num_levels_;
+  int level_count_ = 0;
   std::shared_ptr<b200::DevicePyramid> dev_;  // shared by copies, released with the last one
 };
 
@@ -36,15 +36,15 @@ class DepthPyramid {
  public:
   EIGEN_MAKE_ALIGNED_OPERATOR_NEW
   DepthPyramid() = delete;
-  DepthPyramid(int num_levels, const cv::Mat& in_depth, bool smooth);
+  DepthPyramid(int levels, const cv::Mat& inverse_depth, bool median_level0);
   DepthPyramid& operator=(const DepthPyramid&) = delete;
 
-  int GetNumberLevels() const { return num_levels_; }
-  const cv::Mat& GetPyramidDepth(int level_idx) const;
+  int GetNumberLevels() const { return level_count_; }
+  const cv::Mat& GetPyramidDepth(int level) const;
 
  private:
   friend class LevenbergMarquardtOptimizer;
-  int num_levels_;
+  int level_count_;
   std::shared_ptr<b200::DevicePyramid> dev_;
 };
 
