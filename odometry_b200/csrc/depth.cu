@@ -1149,10 +1149,10 @@ static void launch_disparity_t(odo_ctx* c, int w, int h, const odo_depth_params&
   }
   const size_t esz = QPATH ? sizeof(uint16_t) : sizeof(float);
   const size_t smem = esz * 5 * PITCH + (QPATH ? sizeof(int) * PITCH * (PRUNE ? 4 : 1) : 0) + sizeof(uint16_t) * PITCH;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};  // per device: function attributes are per device
+  if (!attr_done[c->device & 63]) {
     cudaFuncSetAttribute(k_disparity<QPATH, PITCH, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+    attr_done[c->device & 63] = true;
   }
   // one-instruction warp argmin on packed (cost, column) keys: needs 256 * ssd_th below the clamp (see kernel)
   const int key_bits = (PITCH <= 2048) ? 11 : 12;
@@ -1197,10 +1197,10 @@ static size_t refine_smem_bytes(int cap, int G) {
 
 void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};  // per device: function attributes are per device
+  if (!attr_done[c->device & 63]) {
     cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+    attr_done[c->device & 63] = true;
   }
   const int gmax = (d.cap + kRefThreads - 1) / kRefThreads;  // one slot per thread
   // G CTAs per sequence, all co-resident (group barrier).  Fewer CTAs per sequence mean more slots, hence more shared
