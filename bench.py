@@ -5,11 +5,14 @@ A "step" is one pass of the hot path over one batch: one new 1241x376 stereo fra
 independent synthetic sequences resident on the GPU (image pyramid + LM Solve against the keyframe
 + ComputeDepth (selection, SSD disparity search, depth refinement) + depth pyramid + keyframe rule:
 the per-frame body of run_odometry_kitti_offline.cpp:198-271).  With --gpus N every rank runs its
-own S sequences (sharding of independent sequences, no data-path collective => weak scaling).
+own S sequences (sharding of independent sequences, no data-path collective => weak scaling);
+--seqs-total T shards T sequences over the ranks instead (config 4 as written: strong scaling).
 
-  value : frames/s with the step's inputs already resident in HBM (odo_tracker_step_dev)
-  e2e   : frames/s through the reference-facing C-ABI call with HOST buffers (CV_32F images in
-          pinned memory, H2D of the step's frames and D2H of the poses inside the timed region)
+  value : frames/s with the step's inputs already resident in HBM (odo_tracker_enqueue_dev)
+  e2e   : frames/s through the reference-facing C-ABI call with HOST buffers: u8 images in pinned
+          memory (what the reference's imread leaves, run_odometry_kitti_offline.cpp:334-359), H2D of
+          the step's frames and D2H of the poses inside the timed region; the CV_32F variant of the
+          same call is the sub-key e2e.f32_ingest
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: its hot-path sources compiled
 against stand-in Eigen/OpenCV headers; the oracle port if that library is absent) on all host cores, one
@@ -60,6 +63,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=64, help="independent sequences per GPU (batch of one step)")
+    ap.add_argument("--seqs-total", type=int, default=0,
+                    help="config 4 as written: this many sequences IN TOTAL, sharded over the ranks (strong scaling); "
+                         "overrides --seqs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-sequence latency and the 4K (config 5) legs")
+    ap.add_argument("--scene", default="street", choices=["street", "isotropic"],
+                    help="texture spectrum of the synthetic scene (odometry_b200/synth.py); isotropic = the round-1 scene on "
+                         "which the reference's own loop loses track at the first keyframe switch")
     ap.add_argument("--streams", type=int, default=1, help="independent trackers (contexts/streams) per GPU sharing --seqs")
     ap.add_argument("--cpu-seqs", type=int, default=2, help="sequences of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -71,15 +81,31 @@ def parse():
     return ap.parse_args()
 
 
-def config_dict(args, extra=None):
+def seqs_per_gpu(args, world):
+    """(S, scaling): --seqs per GPU (weak) or --seqs-total sharded over the ranks (strong, config 4 as written)."""
+    if args.seqs_total > 0:
+        if args.seqs_total % world:
+            raise SystemExit(f"--seqs-total {args.seqs_total} does not divide over {world} ranks")
+        return args.seqs_total // world, "strong"
+    return args.seqs, "weak"
+
+
+def config_dict(args, world=None, extra=None):
+    world = world or args.gpus
+    S, scaling = seqs_per_gpu(args, world)
     cfg = {
-        "workload": f"config 4/3: {args.seqs} independent synthetic {W}x{H} stereo sequences per GPU, "
-                    f"{LEVELS}-level pyramid, full tracking step per frame (reference-faithful: depth every frame)",
-        "sequences_per_gpu": args.seqs, "frame": f"{W}x{H}", "levels": LEVELS,
+        "workload": f"config 4/3: {S} independent synthetic {W}x{H} stereo sequences per GPU"
+                    + (f" ({args.seqs_total} in total, sharded)" if scaling == "strong" else "")
+                    + f", {LEVELS}-level pyramid, full tracking step per frame (reference-faithful: depth every frame)",
+        "sequences_per_gpu": S, "frame": f"{W}x{H}", "levels": LEVELS,
         "lm": "lambda 0.01, precision 0.995, iters {10,20,30,30}, Huber 28",
         "depth": "grad_th 8, ssd_th 900, photo_th 15, 0.1-30 m, 50 iters, boundary 4",
         "trajectory": "0.8 m/frame forward, yaw 0.4deg*sin(2*pi*t/100), seeds 20190113+sequence_id",
-        "parallelism": f"sequence sharding x{args.gpus} GPUs x{args.streams} trackers per GPU, no collective",
+        "scene": {"street": "street corridor with the anisotropic 'street' spectrum (odometry_b200/synth.py STREET_BANDS: stripes "
+                            "along the driving direction + long-wave structure; documented deviation from SURVEY 8(d), on which "
+                            "the reference's own loop keeps track across keyframe switches)",
+                  "isotropic": "street corridor with the round-1 isotropic spectrum (the reference's loop loses track on it)"}[args.scene],
+        "parallelism": f"sequence sharding x{world} GPUs x{args.streams} trackers per GPU, no collective",
         "l2": "each step reads a fresh batch of frames (S*3.7 MB > 126 MB L2 for S >= 34); no explicit flush",
     }
     if extra:
@@ -126,7 +152,79 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
 
-def render_sequences(seq_ids, n_frames, device):
+def init_dist(dev, world):
+    """NCCL only carries the barrier / max-over-ranks plumbing.  Its INFO log (communicator size, transports) goes to
+    stderr so that stdout stays the one JSON line and the driver can still check the rank count."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+
+
+def _parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank):
+    """Host placement for the e2e legs: run this process on the cores of the NUMA node the GPU hangs off BEFORE the pinned
+    frame buffers are allocated (first touch puts them in that node's memory), so that with 8 ranks the host->device
+    copies do not all cross one socket (every rank sat on cores 0-31 / node 0)."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        info["pci"] = bdf
+        info["numa_node"] = node
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        if node >= 0 and cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+            info["bound"] = True
+        info["cpus"] = len(os.sched_getaffinity(0))
+    except Exception as e:   # placement is best effort (containers without sysfs topology)
+        info["note"] = f"not bound: {type(e).__name__}: {e}"
+    return info
+
+
+def h2d_probe_gbs(dev, stream, mbytes=256):
+    """pinned host -> device copy rate of this rank alone (what bounds the e2e legs)"""
+    import torch
+    host = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        d.copy_(host, non_blocking=True)
+        e1.record(stream)
+        e1.synchronize()
+        best = max(best, (mbytes << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    return hbm_peak, peak_src
+
+
+def render_sequences(seq_ids, n_frames, device, scene="street"):
     """u8 frames [n_frames][len(seq_ids)][2][H][W] on `device` (torch) of the given global sequence ids."""
     import torch
     from odometry_b200 import synth
@@ -134,11 +232,27 @@ def render_sequences(seq_ids, n_frames, device):
     out = torch.empty((n_frames, n_seq, 2, H, W), dtype=torch.uint8, device=device)
     poses = synth.trajectory(n_frames, step=0.8)
     for s, sid in enumerate(seq_ids):
-        sc = synth.make_scene(sid, n_frames, 0.8)
+        sc = synth.make_scene(sid, n_frames, 0.8, bands=synth.ISOTROPIC_BANDS if scene == "isotropic" else synth.STREET_BANDS)
         for f, T in enumerate(poses):
             L, R, _ = synth.render_stereo(sc, T, W, H, device)
             out[f, s, 0], out[f, s, 1] = L, R
     return out
+
+
+def gt_relative_poses(n_frames):
+    """ground-truth pose of frame f in the frame-0 camera (what the tracker's pose_abs estimates)"""
+    from odometry_b200 import synth
+    poses = synth.trajectory(n_frames, step=0.8)
+    P0i = np.linalg.inv(poses[0])
+    return [P0i @ P for P in poses]
+
+
+def pose_error_summary(pose_abs_by_seq, gt):
+    """translation error of the estimated absolute poses ([S][4][4], row/col) against the ground truth 4x4"""
+    err = np.linalg.norm(np.asarray(pose_abs_by_seq)[:, :3, 3] - gt[:3, 3][None, :], axis=1)
+    dist = float(np.linalg.norm(gt[:3, 3]))
+    return {"unit": "m", "path_length_m": dist, "median": float(np.median(err)), "max": float(err.max()),
+            "median_rel": float(np.median(err) / max(dist, 1e-9)), "max_rel": float(err.max() / max(dist, 1e-9))}
 
 
 def cpu_tracker_factory():
@@ -189,45 +303,55 @@ def cpu_tracking_fps(frames_u8, n_seq, n_frames, threads):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    """--impl reference: the reference's own CPU code on all host cores: the SAME sequences-per-step as the GPU arm
+    (config), spread round robin over one worker thread per logical core (the ctypes calls release the GIL)."""
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
-    n_seq = max(1, min(cores, 32))
+    S, scaling = seqs_per_gpu(args, max(world, 1))
+    n_seq = S * max(world, 1)
     n_frames = 1 + args.warmup + args.steps
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    frames = render_sequences(list(range(n_seq)), n_frames, dev).cpu().numpy()
+    frames = render_sequences(list(range(n_seq)), n_frames, dev, args.scene).cpu().numpy()
     kind, make = cpu_tracker_factory()
-    # warm-up steps are part of the same trajectory: time only the last `steps` frames
     trackers = [make() for _ in range(n_seq)]
-    fl = frames.astype(np.float32)
+    threads = max(1, min(cores, n_seq))
+    last = [None] * n_seq
+    n_kf = [0] * n_seq
 
-    def advance(s, f0, f1):
-        for f in range(f0, f1):
-            trackers[s].step(fl[f, s, 0], fl[f, s, 1])
+    def advance(k, f0, f1):
+        for s in range(k, n_seq, threads):
+            for f in range(f0, f1):
+                last[s] = trackers[s].step(frames[f, s, 0].astype(np.float32), frames[f, s, 1].astype(np.float32))
+                n_kf[s] += int(bool(last[s][3])) if f > args.warmup else 0
 
     def parallel(f0, f1):
-        ths = [threading.Thread(target=advance, args=(s, f0, f1)) for s in range(n_seq)]
+        ths = [threading.Thread(target=advance, args=(k, f0, f1)) for k in range(threads)]
         for th in ths:
             th.start()
         for th in ths:
             th.join()
 
+    # warm-up steps are part of the same trajectory: time only the last `steps` frames
     parallel(0, 1 + args.warmup)
     t0 = time.perf_counter()
     parallel(1 + args.warmup, n_frames)
     dt = time.perf_counter() - t0
     fps = n_seq * args.steps / dt
+    gt = gt_relative_poses(n_frames)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, {"sequences_per_step": n_seq}),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": n_seq, "kind": kind,
-                         "sample": f"{n_seq} sequences x {args.steps} frames, one tracker per host thread; " + CPU_KIND_NOTE[kind]},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, max(world, 1)),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{n_seq} sequences x {args.steps} frames over {threads} host threads (round robin); "
+                                   + CPU_KIND_NOTE[kind]},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "frames_per_step": n_seq,
+        "pose_error_vs_gt": pose_error_summary([r[1] for r in last], gt[n_frames - 1]),
+        "keyframes_in_timed_region": int(sum(n_kf)),
     }
     print(json.dumps(line), flush=True)
 
@@ -330,17 +454,30 @@ def run_reference_4k(args, rank):
 def run_4k(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from odometry_b200 import capi, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    init_dist(dev, world)
+    line = measure_4k(args, rank, local_rank, world, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    K, Wm = args.steps, args.warmup
+        dist.destroy_process_group()
+
+
+def measure_4k(args, rank, local_rank, world, K, Wm, do_e2e, do_cpu):
+    """config 5 on this rank's GPU; returns the bench line (also embedded in the default kitti line as config5_4k)"""
+    import torch
+    from odometry_b200 import capi, shard
+
+    dev = torch.device("cuda", local_rank)
     key8, inv, frames8, Kcam = render_4k(rank, Wm + K, dev)
+    from odometry_b200 import synth
+    t_last = Wm + K
+    T_gt_last = synth.relative_pose(synth.pose_from_motion(), synth.pose_from_motion(0.0, 0.0, 0.02 * t_last, 0.0,
+                                                                                      math.radians(0.01 * t_last), 0.0))
     stream = torch.cuda.current_stream(dev)
     ctx = capi.Context(local_rank, stream.cuda_stream)   # the context runs on torch's stream: events below see its work
     p = lm_params_4k(capi, Kcam)
@@ -393,7 +530,7 @@ def run_4k(args, rank, local_rank, world):
     value = world * K / (ms_total * 1e-3)
 
     e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         host = frames_f.cpu().pin_memory()
 
         def step_host(f, T_prev, _):
@@ -409,13 +546,7 @@ def run_4k(args, rank, local_rank, world):
                "host_buffers": "pinned float32 (CV_32F) frame", "api": "odo_image_pyramid_build + odo_lm_solve"}
         del host
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    hbm_peak, peak_src = load_peaks()
     lvl_px = [(W4 >> l) * (H4 >> l) for l in range(LEVELS4)]
     iters = acc["iters"] / K
     lm_bytes = float(sum(12 * lvl_px[l] * iters[l] for l in range(LEVELS4)))   # 12 B per pixel per linearisation
@@ -430,7 +561,7 @@ def run_4k(args, rank, local_rank, world):
             "per_stage_gbs": {"image_pyramid": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "lm_solve": ach}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and do_cpu:
         import oracle
         from oracle import ref
         po = lm_params_4k(oracle, Kcam)
@@ -447,18 +578,16 @@ def run_4k(args, rank, local_rank, world):
         cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": 1, "kind": kind,
                "sample": "1 frame (3 pyramid builds + one cold-started Solve), 1 thread; " + CPU_KIND_NOTE[kind]}
 
-    if rank == 0:
-        line = {"metric": METRIC_4K, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config_4k(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "frames_per_step": world, "all_status_ok": bool(acc["ok"]),
-                "final_pose_translation": [float(x) for x in T_last[:3, 3]]}
-        print(json.dumps(line), flush=True)
+    line = {"metric": METRIC_4K, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_4k(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "frames_per_step": world, "all_status_ok": bool(acc["ok"]),
+            "final_pose_translation": [float(x) for x in T_last[:3, 3]],
+            "pose_error_vs_gt_m": float(np.linalg.norm(T_last[:3, 3] - T_gt_last[:3, 3]))}
     p1.release()
     d1.release()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -554,9 +683,7 @@ def run_rectify(args, rank, local_rank, world):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+    init_dist(dev, world)
     K, Wm = args.steps, args.warmup
     cp, G = rectify_setup()
     stream = torch.cuda.Stream(device=dev)   # a real (non-null) stream: the context runs on it and the events below see its work
@@ -619,13 +746,7 @@ def run_rectify(args, rank, local_rank, world):
                "api": "odo_camera_undistort_rectify_batch (one call per eye; the rectified CV_32F images are the result read back: "
                       "PCIe-bound, 5 bytes per pixel)"}
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    hbm_peak, peak_src = load_peaks()
     launch_ms = ms_total / K / 2
     alg = B * npx * (1 + 4) + 8 * npx      # raw u8 in, CV_32F out, the float2 table once per launch
     ach = alg / (launch_ms * 1e-3) / 1e9
@@ -678,6 +799,10 @@ def main():
         run_rectify(args, rank, local_rank, world)
         return
 
+    run_kitti(args, rank, local_rank, world)
+
+
+def run_kitti(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from odometry_b200 import capi, shard
@@ -686,15 +811,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+    placement = bind_to_gpu_numa(local_rank)     # before any pinned allocation and before NCCL spawns its threads
+    init_dist(dev, world)
 
-    S, K, Wm = args.seqs, args.steps, args.warmup
+    (S, scaling), K, Wm = seqs_per_gpu(args, world), args.steps, args.warmup
     n_frames = 1 + Wm + K
     # config 4: world*S independent sequences, sequence s on rank s mod world (odometry_b200/shard.py)
     seq_ids = shard.shard_sequences(world * S, world, rank)
-    frames_u8 = render_sequences(seq_ids, n_frames, dev)                # [F][S][2][H][W] u8 on device
+    frames_u8 = render_sequences(seq_ids, n_frames, dev, args.scene)    # [F][S][2][H][W] u8 on device
+    gt = gt_relative_poses(n_frames)
     stream = torch.cuda.current_stream(dev)
     # T trackers per GPU, each with its own context (= its own CUDA streams) and S/T of the sequences.  A
     # frame is a dependent chain of kernels, some throughput bound (disparity search), some latency bound
@@ -729,7 +854,7 @@ def main():
                 res = t.collect()
                 assert res[0] == 0, "tracking failed"
                 if on_result:
-                    on_result(t, res)
+                    on_result(t, i, f, res)
 
     def timed(fn):
         """Device time of fn() between two idle points: e0 is recorded with the GPU idle, e1 after the host
@@ -755,11 +880,14 @@ def main():
     run_pipelined(trks, enq_dev, 0, 1 + Wm)
     sampler = ClockSampler(local_rank)
     stage_acc, tally = {}, {"kf": 0, "ok": True}
+    final_pose = np.zeros((S, 4, 4), np.float32)
 
-    def on_result(t, res):
+    def on_result(t, i, f, res):
         rc, pa, pk, kf, st = res
         tally["kf"] += int(kf.sum())
         tally["ok"] &= bool((st == 0).all())
+        if f == n_frames - 1:
+            final_pose[i * St:(i + 1) * St] = pa
         for k, v in t.stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / T
 
@@ -769,7 +897,14 @@ def main():
     clocks = sampler.result()
     launches = launch_total() - launches0
     value = world * S * K / (ms_total * 1e-3)
-    n_kf, status_ok = tally["kf"], tally["ok"]
+    n_kf = int(shard.sum_over_ranks(tally["kf"], dev))
+    status_ok = bool(shard.sum_over_ranks(0.0 if tally["ok"] else 1.0, dev) == 0.0)
+    pose_err = pose_error_summary(final_pose, gt[n_frames - 1])
+    pose_err["max"] = shard.max_over_ranks(pose_err["max"], dev)
+    pose_err["max_rel"] = shard.max_over_ranks(pose_err["max_rel"], dev)
+    pose_err["note"] = (f"translation error of pose_abs after frame {n_frames - 1} of every sequence (device-resident leg); median of "
+                        "rank 0's sequences, max over all ranks; the reference itself drifts by about 1 % of the path (floor() "
+                        "sampling), see pose_error_vs_gt of --impl reference")
     for t in trks:
         t.close()
     del left_dev, right_dev
@@ -777,50 +912,46 @@ def main():
     # ---------------- leg 2: end to end through the C-ABI with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        host = frames_u8.to(torch.float32).cpu().pin_memory()           # [F][S][2][H][W] pinned CV_32F frames
-        trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
+        def e2e_leg(host, u8):
+            trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
 
-        def enq_host(t, i, f):
-            base = host[f, i * St:(i + 1) * St]
-            t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)])
+            def enq_host(t, i, f):
+                base = host[f, i * St:(i + 1) * St]
+                t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)], u8=u8)
 
-        run_pipelined(trks, enq_host, 0, 1 + Wm)
-        ms_e2e = timed(lambda: run_pipelined(trks, enq_host, 1 + Wm, n_frames))
+            run_pipelined(trks, enq_host, 0, 1 + Wm)
+            ms = timed(lambda: run_pipelined(trks, enq_host, 1 + Wm, n_frames))
+            for t in trks:
+                t.close()
+            return ms
+
+        # the frames as the reference's imread(GRAYSCALE) leaves them: u8, one pinned buffer per image
+        host8 = frames_u8.cpu().pin_memory()                            # [F][S][2][H][W] u8
+        ms_e2e = e2e_leg(host8, True)
+        del host8
+        h2d = S * 2 * W * H
         e2e = {"value": world * S * K / (ms_e2e * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": S * 2 * W * H * 4, "d2h_bytes_per_step": S * 240,
-               "ms_per_step": ms_e2e / K, "host_buffers": "pinned float32 (CV_32F), one pointer per image",
-               "api": "odo_tracker_enqueue + odo_tracker_collect (two frames in flight per tracker: the copy of "
-                      "frame f+1 overlaps the kernels of frame f; every frame's poses are read back)"}
-        for t in trks:
-            t.close()
-        # fused u8 ingest (row f2 of SURVEY 8f): same call with the frames as the PNG decoder leaves them
-        host8 = frames_u8.cpu().pin_memory()
-        trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
-
-        def enq_host8(t, i, f):
-            base = host8[f, i * St:(i + 1) * St]
-            t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)], u8=True)
-
-        run_pipelined(trks, enq_host8, 0, 1 + Wm)
-        ms_u8 = timed(lambda: run_pipelined(trks, enq_host8, 1 + Wm, n_frames))
-        e2e["u8_ingest"] = {"value": world * S * K / (ms_u8 * 1e-3), "unit": "frames/s",
-                            "h2d_bytes_per_step": S * 2 * W * H}
-        for t in trks:
-            t.close()
-        del host, host8
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": S * 240,
+               "ms_per_step": ms_e2e / K, "host_buffers": "pinned u8 (what imread(GRAYSCALE) returns), one pointer per image",
+               "api": "odo_tracker_enqueue_u8 + odo_tracker_collect (two frames in flight per tracker: the copy of "
+                      "frame f+1 overlaps the kernels of frame f; the convertTo(CV_32F) of run_odometry_kitti_offline.cpp:348 "
+                      "runs on the device; every frame's poses are read back)",
+               "frac_of_device_rate": ms_total / ms_e2e,
+               "h2d_gbs_achieved_per_rank": h2d * K / (ms_e2e * 1e-3) / 1e9,
+               "h2d_gbs_probe_this_rank": h2d_probe_gbs(dev, stream),
+               "host_placement": placement}
+        host = frames_u8.to(torch.float32).cpu().pin_memory()           # the same call with CV_32F frames (4x the bytes)
+        ms_f32 = e2e_leg(host, False)
+        del host
+        e2e["f32_ingest"] = {"value": world * S * K / (ms_f32 * 1e-3), "unit": "frames/s",
+                             "h2d_bytes_per_step": S * 2 * W * H * 4, "api": "odo_tracker_enqueue (CV_32F host frames)"}
 
     # ---------------- roofline of the dominant kernel (device-resident leg, this rank) ----------------
     # Stage times are CUDA-event intervals on the stream each stage runs on, averaged over the timed steps.
     # The LM solve runs on its own stream CONCURRENTLY with blur_select + disparity (+ refine), so the stages
     # do not add up to the step; the critical path is image_pyramid -> blur_select -> disparity ->
     # depth_refine -> prepare, and the dominant kernel is taken among those.
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    hbm_peak, peak_src = load_peaks()
     stage_ms = {k: v / K for k, v in stage_acc.items()}
     npx = W * H
     pyr_px = sum((W >> l) * (H >> l) for l in range(LEVELS))
@@ -850,7 +981,9 @@ def main():
             "algorithmic_bytes_per_launch": alg_bytes[dom] * St, "sequences_per_launch": St,
             "stage_ms_per_step": stage_ms,
             "stages_overlap": "lm_solve runs on a second stream concurrently with blur_select/disparity/depth_refine",
-            "per_stage_gbs": {k: alg_bytes[k] * St / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)}}
+            "per_stage_gbs": {k: alg_bytes[k] * St / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)},
+            "hbm_note": "frac = algorithmic HBM bytes of the dominant kernel / its time / HBM peak (the contract's definition); "
+                        "the line search is bound by instruction issue, not HBM: see issue_roofline"}
     if dom == "disparity":
         # the line search is bound by integer-multiply issue, not by HBM: 8 IMAD per (pixel, candidate) on the
         # half-rate fmaheavy pipe (ncu: sm__pipe_fmaheavy_cycles_active).  Candidate evaluations of one frame are
@@ -865,20 +998,52 @@ def main():
             clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
             peak_evals = sm * 4 * 16 * clk / 8.0              # 16 IMAD lanes per scheduler per clock, 8 IMAD per evaluation
             ach_evals = evals * St / (stage_ms[dom] * 1e-3)
-            roof["issue_roofline"] = {"bound": "imad (fmaheavy pipe)", "unit": "candidate evaluations/s",
-                                      "note": "evaluations = the reference's (pixel, candidate) count; peak = 8 IMAD each at the "
-                                              "fmaheavy issue rate; the pruned scan rejects most candidates from a 2-IDP4A bound",
+            roof["issue_roofline"] = {"bound": "issue", "pipe": "imad (fmaheavy)", "unit": "candidate evaluations/s",
+                                      "note": "ALGORITHMIC-work figure: evaluations = the reference's (pixel, candidate) count, "
+                                              "peak = 8 IMAD each at the fmaheavy issue rate; the pruned scan does NOT perform "
+                                              "most of them (it rejects whole chunks from a 2-IDP4A bound), so this is achieved "
+                                              "algorithmic work per second against the brute-force issue peak, not pipe utilisation "
+                                              "(ncu: profiles/ncu_*_summary.md)",
                                       "evaluations_per_frame": evals, "achieved": ach_evals, "peak": peak_evals,
                                       "frac": ach_evals / peak_evals}
         except Exception as e:  # the probe is informational
             roof["issue_roofline"] = {"error": str(e)}
+
+    # ---------------- extras: single-sequence latency (north-star target < 1 ms) and config 5 ----------------
+    latency = None
+    cfg5 = None
+    if not args.no_extras:
+        trk1 = capi.Tracker(ctx, W, H, LEVELS, 1)
+        l1 = frames_u8[:, 0, 0].to(torch.float32).contiguous()
+        r1 = frames_u8[:, 0, 1].to(torch.float32).contiguous()
+        for f in range(0, 1 + Wm):
+            assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr())[0] == 0
+
+        def lat():
+            for f in range(1 + Wm, n_frames):
+                assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr())[0] == 0     # one frame at a time: enqueue + collect
+
+        ms_lat = timed(lat)
+        latency = {"latency_s1_ms": ms_lat / K, "frames": K,
+                   "what": "one 1241x376 stereo frame of ONE sequence, step by step (odo_tracker_step_dev: the pose is read back "
+                           "before the next frame is queued): pyramid + Solve + ComputeDepth + keyframe rule"}
+        trk1.close()
+        del l1, r1
+    del frames_u8
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        l5 = measure_4k(args, rank, local_rank, world, 5, 3, False, False)
+        cfg5 = {"value": l5["value"], "unit": l5["unit"], "ms_per_step": l5["ms_per_step"], "steps": 5, "warmup": 3,
+                "roofline": l5["roofline"], "all_status_ok": l5["all_status_ok"], "pose_error_vs_gt_m": l5["pose_error_vs_gt_m"],
+                "config": l5["config"]["workload"]}
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_seqs, S)
         nf = min(n_frames, 1 + 30)
-        fps, nfr, kind = cpu_tracking_fps(frames_u8[:nf, :ns].cpu().numpy(), ns, nf, threads=1)
+        fr = render_sequences(seq_ids[:ns], nf, dev, args.scene).cpu().numpy()
+        fps, nfr, kind = cpu_tracking_fps(fr, ns, nf, threads=1)
         cpu = {"value": fps, "unit": "frames/s", "cores": 1, "kind": kind,
                "sample": f"{ns} sequences x {nf - 1} frames of the same workload, 1 thread "
                          f"(host has {os.cpu_count()} logical cores); " + CPU_KIND_NOTE[kind]}
@@ -886,12 +1051,18 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "frames_per_step": world * S, "keyframes_in_timed_region": n_kf, "all_status_ok": status_ok,
+            "frames_per_step": world * S, "keyframes_in_timed_region": n_kf,
+            "keyframe_fraction": n_kf / float(world * S * K), "all_status_ok": status_ok,
+            "pose_error_vs_gt": pose_err,
             "disparity_mpix_per_s": (npx * S / 1e6) / ((stage_ms["blur_select"] + stage_ms["disparity"] + stage_ms["depth_refine"]) * 1e-3),
         }
+        if latency:
+            line.update(latency)
+        if cfg5:
+            line["config5_4k"] = cfg5
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()

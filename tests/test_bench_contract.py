@@ -23,11 +23,15 @@ def run_reference(*extra):
 
 @pytest.mark.parametrize("workload,unit", [("kitti", "frames/s"), ("rectify", "pairs/s")])
 def test_reference_arm_line(workload, unit):
-    d = run_reference("--workload", workload, "--steps", "1", "--warmup", "0")
+    d = run_reference("--workload", workload, "--steps", "1", "--warmup", "0", "--seqs", "3")
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
     assert d["impl"] == "reference" and d["unit"] == unit and d["higher_is_better"] is True and d["scaling"] == "weak"
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["value"] > 0 and d["ms_per_step"] > 0
     assert "workload" in d["config"]
+    if workload == "kitti":
+        # the reference arm runs the SAME number of sequences per step as the GPU arm's config (same_config)
+        assert d["config"]["sequences_per_gpu"] == 3 and d["frames_per_step"] == 3
+        assert d["pose_error_vs_gt"]["max"] < 0.05      # one 0.8 m frame from the keyframe: centimetres
     cb = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] in ("reference", "port")
     assert cb["value"] == d["value"] and cb["cores"] >= 1 and "host:" in cb["sample"]

@@ -166,3 +166,29 @@ def test_dense_4k_linearize(ctx):
         assert got["N"] == wide["N"]
         assert rel_err(got["H"], wide["H"]) < 1e-11
         assert rel_err(got["g"], wide["g"]) < 1e-9
+
+
+def test_dense_4k_solve_matches_oracle(ctx):
+    """Config 5: one 3840x2160 frame, 6-level pyramids, all-pixel dense alignment -- the whole coarse-to-fine Solve
+    (src/lm_optimizer.cpp:73-160, iters {10,20,30,30,30,30}) against the oracle in ORC_SUM_WIDE."""
+    from odometry_b200 import synth
+    sc = synth.make_scene(1000, 2)
+    kw = dict(w=3840, h=2160, device="cuda", fx=synth.FX, cx=synth.CX, cy=synth.CY)   # the reference's hard-coded camera
+    T1 = synth.pose_from_motion()
+    T2 = synth.pose_from_motion(0.0, 0.0, 0.06, 0.0, math.radians(0.03), 0.0)
+    L1, z1 = synth.render(sc, T1, **kw)
+    L2, _ = synth.render(sc, T2, **kw)
+    L1, L2 = L1.cpu().numpy().astype(np.float32), L2.cpu().numpy().astype(np.float32)
+    dep = (1.0 / z1.cpu().numpy()).astype(np.float32)
+    iters = (10, 20, 30, 30, 30, 30)
+    p1, d1, p2 = ctx.image_pyramid(L1, 6, True), ctx.depth_pyramid(dep, 6, False), ctx.image_pyramid(L2, 6, True)
+    rc, T, st = ctx.lm_solve(p1, d1, p2, capi.default_lm_params(max_iters=iters))
+    orc, oT, ost = oracle.lm_solve(oracle.image_pyramid(L1, 6, True, packed=True), oracle.depth_pyramid(dep, 6, False, packed=True),
+                                   oracle.image_pyramid(L2, 6, True, packed=True), 3840, 2160, 6, oracle.lm_params(max_iters=iters))
+    assert rc == orc == 0
+    assert list(st.iters)[:6] == list(ost.iters)[:6] and list(st.n_res)[:6] == list(ost.n_res)[:6]
+    ang, tr = pose_err(T, oT)
+    assert ang < 1e-4 and tr < 1e-4, (ang, tr)
+    gt = synth.relative_pose(T1, T2).astype(np.float32)
+    ang, tr = pose_err(T, gt)
+    assert tr < 5e-3 and ang < 1e-3, (ang, tr)

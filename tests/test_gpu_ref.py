@@ -99,11 +99,11 @@ def test_solve_vs_reference(ctx, pair):
     assert ang < 1e-4 and np.linalg.norm(T[:3, 3] - rT[:3, 3]) < 1e-3
 
 
-def test_tracking_vs_reference_until_keyframe_switch(synth_data):
-    """The batched device tracker against the loop over the reference's classes.  Up to the first keyframe
-    switch the poses agree to the association bound; after it the reference warm-starts from the pose to the OLD
-    keyframe (quirk A.8) and the trajectories of any two summation orders drift apart."""
-    seq = synth_data.sequence(0, 5)
+def test_tracking_vs_reference_across_a_keyframe_switch(synth_data):
+    """The batched device tracker against the loop over the reference's classes, across the first keyframe switch
+    (frame 5) and the warm start with the pose to the OLD keyframe that follows it (quirk A.8); the 100-frame version
+    is tests/test_gpu_long.py."""
+    seq = synth_data.sequence(0, 8)
     c = capi.Context(0)
     trk = capi.Tracker(c, W, H, LEVELS, 1)
     rt = ref.Tracker(W, H, LEVELS, oracle.lm_params(sum_mode=oracle.SUM_FLOAT_SEQ), oracle.depth_params(sum_mode=oracle.SUM_FLOAT_SEQ))
