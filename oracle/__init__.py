@@ -16,6 +16,8 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 SUM_FLOAT_SEQ = 0
 SUM_WIDE = 1
+SUM_PACKET4 = 2     # oracle/_ref only: other legal fp32 associations of the N-term products
+SUM_PAIRWISE = 3    # (tools/association_noise.py)
 
 
 def build(force: bool = False) -> str:

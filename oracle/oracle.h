@@ -74,7 +74,8 @@ void orc_mat4_mul(const float A[16], const float B[16], float C[16]);
 void orc_solve6(const float A_colmajor[36], const float b[6], float x[6]);
 
 /* ---- LM direct alignment -------------------------------------------------------------------- */
-enum { ORC_SUM_FLOAT_SEQ = 0, ORC_SUM_WIDE = 1 };
+/* PACKET4 / PAIRWISE: other legal fp32 associations, understood by oracle/_ref only (association-noise measurement) */
+enum { ORC_SUM_FLOAT_SEQ = 0, ORC_SUM_WIDE = 1, ORC_SUM_PACKET4 = 2, ORC_SUM_PAIRWISE = 3 };
 
 typedef struct {
   float lambda;          /* lambda_ */

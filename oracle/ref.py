@@ -85,7 +85,7 @@ def lm_linearize(I1, I2, D1, level, T, robust=1, huber_delta=28.0, sum_mode=SUM_
     jac = np.zeros((w * h, 6), np.float32)
     wgt = np.zeros(w * h, np.float32)
     rc = lib().ref_lm_linearize(_p(I1), _p(I2), _p(D1), w, h, level, _p(_colmajor(T)), robust, C.c_float(huber_delta),
-                                int(sum_mode == SUM_WIDE), _p(H, C.c_double), _p(g, C.c_double), C.byref(E), C.byref(N),
+                                int(sum_mode), _p(H, C.c_double), _p(g, C.c_double), C.byref(E), C.byref(N),
                                 _p(res), _p(jac), _p(wgt))
     n = N.value
     return dict(rc=rc, H=H, g=g, E=E.value, N=n, res=res[:n], jac=jac[:n], wgt=wgt[:n])

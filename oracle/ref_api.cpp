@@ -109,7 +109,7 @@ int ref_lm_linearize(const float* I1, const float* I2, const float* D1, int w, i
                      int robust, float huber_delta, int sum_wide, double H21[21], double g6[6], double* E, int* N,
                      float* res_out, float* jac_out, float* wgt_out) {
   Quiet q;
-  odo_ref_shim::sum_wide() = sum_wide != 0;
+  odo_ref_shim::sum_mode() = sum_wide;   // ORC_SUM_*
   float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   LevenbergMarquardtOptimizer opt(0.01f, 0.995f, std::vector<int>{1, 1, 1, 1, 1, 1, 1, 1}, to_affine(I), nullptr, robust,
                                   huber_delta);
@@ -144,7 +144,7 @@ int ref_lm_linearize(const float* I1, const float* I2, const float* D1, int w, i
 int ref_lm_solve(const float* img1, int smooth1, const float* dep1, const float* img2, int smooth2, int w, int h, int levels,
                  const orc_lm_params* p, const float T_init[16], float T_out[16]) {
   Quiet q;
-  odo_ref_shim::sum_wide() = p->sum_mode == ORC_SUM_WIDE;
+  odo_ref_shim::sum_mode() = p->sum_mode;
   ImagePyramid p1(levels, wrap(img1, w, h), smooth1 != 0);
   DepthPyramid d1(levels, wrap(dep1, w, h), false);
   ImagePyramid p2(levels, wrap(img2, w, h), smooth2 != 0);
@@ -225,7 +225,7 @@ ref_tracker* ref_tracker_create(int w, int h, int levels, const orc_lm_params* l
   t->depth = make_depth(dp);
   const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   t->lm = make_lm(lm, levels, I);
-  odo_ref_shim::sum_wide() = lm->sum_mode == ORC_SUM_WIDE;
+  odo_ref_shim::sum_mode() = lm->sum_mode;
   t->kf_pose_abs = to_affine(I);
   t->cur_pose = to_affine(I);
   t->frame_id = 0;

@@ -193,3 +193,26 @@ def test_tracking_loop_bit_exact(synth_data):
     assert kfs >= 2
     a.close()
     b.close()
+
+
+def test_other_legal_associations_of_the_reference_sums(pair):
+    """oracle/_ref can add the reference's N-term float products in four legal orders (ref_shim/Eigen/Core): they must be
+    the same sums up to rounding, and the converged poses must stay within millimetres of each other -- the association
+    noise of the reference itself, measured over 20 pairs in profiles/association_noise_r2.json."""
+    o1 = oracle.image_pyramid(pair["L1"], LEVELS, True)
+    o2 = oracle.image_pyramid(pair["L2"], LEVELS, True)
+    od = oracle.depth_pyramid(pair["dep"], LEVELS, False)
+    T = _poses(pair)[2]
+    base = ref.lm_linearize(o1[0], o2[0], od[0], 0, T, 1, 28.0, oracle.SUM_WIDE)
+    for mode in (oracle.SUM_FLOAT_SEQ, oracle.SUM_PACKET4, oracle.SUM_PAIRWISE):
+        r = ref.lm_linearize(o1[0], o2[0], od[0], 0, T, 1, 28.0, mode)
+        assert r["N"] == base["N"]
+        assert np.abs(r["H"] - base["H"]).max() <= 3e-5 * np.abs(base["H"]).max()
+        assert not np.array_equal(r["H"], base["H"])         # a different rounding, not the same code path
+    sols = []
+    for mode in (oracle.SUM_FLOAT_SEQ, oracle.SUM_WIDE, oracle.SUM_PACKET4, oracle.SUM_PAIRWISE):
+        rc, Tm = ref.lm_solve(pair["L1"], pair["dep"], pair["L2"], LEVELS, oracle.lm_params(robust=1, sum_mode=mode))
+        assert rc == 0
+        sols.append(Tm)
+    spread = max(np.linalg.norm(a[:3, 3] - b[:3, 3]) for a in sols for b in sols)
+    assert spread < 2e-2
