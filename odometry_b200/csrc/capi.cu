@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -233,6 +234,10 @@ static int lm_group_size(const odo_ctx* c, const PyrGeom& g) {
   int G = (int)((n0 + 16383) / 16384);
   const int cap = lm_max_ctas(c);
   if (G > cap) G = cap;
+  if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // test / experiment knob (the tracker reads it too)
+    const int g = std::atoi(e);
+    if (g >= 1 && g <= cap) G = g;
+  }
   if (G < 1) G = 1;
   return G;
 }
@@ -261,25 +266,39 @@ static int lm_run(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_py
   const bool lists_cached = !lists_realloc && c->lists_img_id == i1->id && c->lists_dep_id == d1->id &&
                             c->lists_K.fx == p->K.fx && c->lists_K.cx == p->K.cx && c->lists_K.cy == p->K.cy;
   if (!lists_cached) {
-    launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr);
+    // the cache ids are only valid for lists that were really built: cleared first, set after the launches succeeded
+    c->lists_img_id = c->lists_dep_id = 0;
+    if (launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr) != 0) return -1;
     c->lists_img_id = i1->id;
     c->lists_dep_id = d1->id;
     c->lists_K = p->K;
   }
-  if (launch_lm_solve(c, L, i2->d, 0, g, *p, T_dev, res_dev, wk, 1, G, only_level) != 0) return -1;
-  ODO_CUDA_OK(c, cudaMemcpyAsync(host_res, res_dev, sizeof(LmResult), cudaMemcpyDeviceToHost, c->stream));
-  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (launch_lm_solve(c, L, i2->d, 0, g, *p, T_dev, res_dev, wk, 1, G, only_level) != 0) {
+    c->lists_img_id = c->lists_dep_id = 0;
+    return -1;
+  }
+  cudaError_t e = cudaMemcpyAsync(host_res, res_dev, sizeof(LmResult), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    c->err = std::string("lm_solve: ") + cudaGetErrorString(e);
+    c->lists_img_id = c->lists_dep_id = 0;
+    return -1;
+  }
   return 0;
 }
 
 int odo_lm_solve(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_pyr* i2, const odo_lm_params* p,
                  const float T_init[16], float T_out[16], odo_lm_stats* st) {
   if (!p || !T_init || !T_out) return -1;
-  if (lm_check(c, i1, d1, i2) != 0) {
-    for (int i = 0; i < 16; i++) T_out[i] = 0.f;
-    T_out[0] = T_out[5] = T_out[10] = 1.f;
-    return -1;
+  // whatever fails below, the caller holds the reference's failure value (identity rotation, zero last column,
+  // src/lm_optimizer.cpp:48-52,60-64) and zeroed statistics
+  for (int i = 0; i < 16; i++) T_out[i] = 0.f;
+  T_out[0] = T_out[5] = T_out[10] = 1.f;
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->status = -1;
   }
+  if (lm_check(c, i1, d1, i2) != 0) return -1;
   LmResult res;
   if (lm_run(c, i1, d1, i2, p, T_init, -1, &res) != 0) return -1;
   std::memcpy(T_out, res.T, sizeof(float) * 16);
@@ -289,10 +308,10 @@ int odo_lm_solve(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_pyr
       st->n_res[l] = res.n_res[l];
       st->err[l] = res.err[l];
     }
-    st->status = res.status;
+    st->status = res.status;   // -1: the reference's own failure; -2: a group barrier of the kernel timed out
   }
-  if (res.status != 0) c->err = "Optimize failed! ";
-  return res.status;
+  if (res.status != 0) c->err = (res.status == -2) ? "lm_solve: group barrier timed out (CTAs not co-resident?)" : "Optimize failed! ";
+  return res.status == 0 ? 0 : -1;
 }
 
 int odo_lm_linearize(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_pyr* i2, int level,
@@ -313,7 +332,7 @@ int odo_lm_linearize(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo
   if (E) *E = lo.E;
   if (N) *N = lo.N;
   if (sigma) *sigma = lo.sigma;
-  return res.status;
+  return res.status == 0 ? 0 : -1;
 }
 
 }  // extern "C"

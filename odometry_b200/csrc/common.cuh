@@ -115,8 +115,8 @@ size_t lm_lists_bytes(const PyrGeom& g, int batch, LmLists* layout);  // fills o
 void lm_lists_bind(LmLists* L, void* mem, const PyrGeom& g, int batch);
 // dep_from_l0: dep_pyr holds only level 0 of each sequence's depth pyramid (levels 1.. are read through the
 // odd-pixel subsampling rule)
-void launch_lm_prepare(odo_ctx* c, const float* img_pyr, int64_t istride, const float* dep_pyr, int64_t dstride,
-                       const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active, int dep_from_l0 = 0);
+int launch_lm_prepare(odo_ctx* c, const float* img_pyr, int64_t istride, const float* dep_pyr, int64_t dstride,
+                      const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active, int dep_from_l0 = 0);
 
 struct LmLevelOut {      // sums of the last evaluation at a level (test hook / stats)
   double H[21];
@@ -140,8 +140,12 @@ struct LmWork {          // device scratch of the solve kernel
   unsigned* barrier;     // [batch]
   float4* resid;         // [batch][cap] r, gx, gy, valid (t-dist two-phase)
   int64_t resid_stride;
-  int* abort_flag;
+  int* abort_flag;       // [batch]: a sequence whose group barrier timed out (group_sync.cuh)
 };
+// wait bound of the group barriers in ns (env ODO_BARRIER_TIMEOUT_MS, default 2000 ms) and the test hook that makes
+// the last CTA of every group leave at once (env ODO_TEST_LOSE_CTA=1: the barrier-timeout path, tests only)
+unsigned long long group_timeout_ns();
+int group_test_lose_cta();
 // G = CTAs per sequence (1 .. sm_count).  only_level >= 0: evaluate that level once at exactly T_init
 // (test hook for odo_lm_linearize).
 int launch_lm_solve(odo_ctx* c, const LmLists& L, const float* img2_pyr, int64_t i2stride, const PyrGeom& g,
@@ -181,6 +185,10 @@ struct DepthWork {
   uint8_t* rawR8_own;
   int* raw_exact;      // [batch]
   long long* dbg;      // [16] cycle counters of sequence 0 / CTA 0 of the refinement (profiling aid)
+  // SMs held by another persistent kernel that runs CONCURRENTLY with the refinement (the tracker's LM solve on its own
+  // stream: one 512-thread CTA fills an SM's register file).  The refinement's group of co-resident CTAs is sized for
+  // the SMs that are left, so its cooperative launch does not have to wait for the other kernel to drain.
+  int busy_sms;
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)

@@ -867,7 +867,8 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
 __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
                                                           int64_t stride, int W, int H, odo_depth_params p,
                                                           DepthWork d, double* partials, unsigned* barrier,
-                                                          int* abort_flag, int jb_in_smem) {
+                                                          int* abort_flags, int jb_in_smem,
+                                                          unsigned long long timeout_ns, int lose_cta) {
   __shared__ RefShared sh;
   extern __shared__ float2 s_jb[];  // refine_smem_bytes(): {jtwj, b} of every slot this CTA owns
   const int b = blockIdx.y;
@@ -875,10 +876,13 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   GroupSync gs;
   gs.partials = partials + (int64_t)b * 2 * G * 32;
   gs.counter = barrier + b;
-  gs.abort_flag = abort_flag;
+  gs.abort_flag = abort_flags + b;
+  gs.timeout_ns = timeout_ns;
   gs.target = 0;
   gs.parity = 0;
   gs.G = G;
+  int* abort_flag = gs.abort_flag;
+  if (lose_cta && G > 1 && blockIdx.x == G - 1) return;   // test hook: a CTA that never arrives
   const int64_t npx = (int64_t)W * H;
   odo_depth_stats* stats = d.stats + b;
   float* dep = d.dep + b * d.dep_stride;
@@ -986,7 +990,8 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
     stats->iters = iter_count;
     stats->cost = err_now;
     int status = (n_valid < 500) ? -1 : 0;  // :192-197
-    if (too_many || *(volatile int*)abort_flag) status = -1;
+    if (too_many) status = -1;
+    if (*(volatile int*)abort_flag) status = ODO_STATUS_BARRIER_TIMEOUT;   // not a failure of the algorithm: reported apart
     stats->status = status;
     if (b == 0 && d.dbg) {
       d.dbg[0] = cyc_first; d.dbg[1] = cyc_pass; d.dbg[2] = cyc_red; d.dbg[3] = t_loop_end - t_begin;
@@ -1045,6 +1050,7 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
   d->rawR8_own = (uint8_t*)p; p += al(npx);
   d->raw_exact = (int*)p; p += al((size_t)batch * 4);
   d->dbg = (long long*)p;
+  d->busy_sms = 0;
   d->rawR8 = nullptr;      // set per call: the u8 ingest path points it at the frame it already has
   d->rawR8_stride = (int64_t)w * h;
   d->cap = kGridBlocks * kSelMax;
@@ -1205,13 +1211,22 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
   const int gmax = (d.cap + kRefThreads - 1) / kRefThreads;  // one slot per thread
   // G CTAs per sequence, all co-resident (group barrier).  Fewer CTAs per sequence mean more slots, hence more shared
   // memory, per CTA, which can lower the occupancy again: settle from the register-limited value downwards.
+  // SMs this launch can count on: all of them, minus the ones a concurrently running persistent kernel holds -- but only
+  // while that still leaves the refinement most of the device; a large batch keeps the whole-device sizing (its LM
+  // solve has finished by the time the refinement starts, and fewer CTAs per sequence would only slow the passes)
+  int free_sms = c->sm_count;
+  if (d.busy_sms > 0 && d.busy_sms * 2 <= c->sm_count + 2 && !std::getenv("ODO_REFINE_WHOLE_DEVICE")) free_sms -= d.busy_sms;
   int G = gmax;
+  if (const char* e = std::getenv("ODO_REFINE_CTAS_PER_SEQ")) {  // test / experiment knob
+    const int g = std::atoi(e);
+    if (g >= 1 && g < G) G = g;
+  }
   size_t smem = refine_smem_bytes(d.cap, G);
   for (int it = 0; it < 8; it++) {
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, smem);
     if (per_sm < 1) per_sm = 1;
-    int g2 = (c->sm_count * per_sm) / (batch > 0 ? batch : 1);
+    int g2 = (free_sms * per_sm) / (batch > 0 ? batch : 1);
     if (g2 > gmax) g2 = gmax;
     if (g2 < 1) g2 = 1;
     if (g2 >= G) break;
@@ -1225,10 +1240,10 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
     smem = 0;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refine, kRefThreads, 0);
-    G = std::max(1, std::min(gmax, (c->sm_count * std::max(per_sm, 1)) / (batch > 0 ? batch : 1)));
+    G = std::max(1, std::min(G, (free_sms * std::max(per_sm, 1)) / (batch > 0 ? batch : 1)));
   }
   // partials / barrier / abort flag: carved from a small dedicated allocation owned by the context
-  const size_t need = al(sizeof(double) * 2 * (size_t)G * 32 * batch) + al(sizeof(unsigned) * batch) + 256;
+  const size_t need = al(sizeof(double) * 2 * (size_t)G * 32 * batch) + al(sizeof(unsigned) * batch) * 2;
   if (c->scratch_bytes[15] < need) {
     if (c->scratch[15]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[15]); }
     c->scratch[15] = nullptr;
@@ -1240,7 +1255,9 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
   double* partials = (double*)q; q += al(sizeof(double) * 2 * (size_t)G * 32 * batch);
   unsigned* barrier = (unsigned*)q; q += al(sizeof(unsigned) * batch);
   int* abort_flag = (int*)q;
-  cudaMemsetAsync(barrier, 0, al(sizeof(unsigned) * batch) + 256, c->stream);
+  cudaMemsetAsync(barrier, 0, al(sizeof(unsigned) * batch) * 2, c->stream);   // counters and per-sequence abort flags
+  unsigned long long timeout_ns = group_timeout_ns();
+  int lose_cta = group_test_lose_cta();
   if (d.rawR8 == nullptr && d.rawR8_own != nullptr) {
     // float ingest: derive the u8 plane (and learn per sequence whether it is exact)
     const int64_t npx = (int64_t)w * h;
@@ -1257,10 +1274,12 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
     int64_t st = stride;
     odo_depth_params pp = p;
     void* args[] = {(void*)&L, (void*)&R, (void*)&st, (void*)&W, (void*)&H, (void*)&pp, (void*)&d,
-                    (void*)&partials, (void*)&barrier, (void*)&abort_flag, (void*)&jb_in_smem};
+                    (void*)&partials, (void*)&barrier, (void*)&abort_flag, (void*)&jb_in_smem,
+                    (void*)&timeout_ns, (void*)&lose_cta};
     e = cudaLaunchCooperativeKernel((const void*)k_refine, grid, block, args, smem, c->stream);
   } else {
-    k_refine<<<grid, block, smem, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag, jb_in_smem);
+    k_refine<<<grid, block, smem, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag, jb_in_smem, timeout_ns,
+                                               lose_cta);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) c->err = std::string("k_refine launch: ") + cudaGetErrorString(e);

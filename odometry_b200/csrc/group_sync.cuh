@@ -2,7 +2,7 @@
 //
 // Each CTA reduces its values with a fixed shuffle tree and a fixed-order sum over warps, publishes
 // the partial in a double-buffered global array, meets the other CTAs of its group at a counter
-// barrier and then sums the G partials in index order.  Every CTA ends up with bit-identical totals,
+// barrier and then sums the G partials in a fixed order.  Every CTA ends up with bit-identical totals,
 // so the replicated control flow (accept/reject, convergence) stays in lock step without a second
 // barrier.  G == 1 never touches global memory.  Kernels using G > 1 are launched cooperatively so
 // that all CTAs of a group are co-resident.
@@ -11,10 +11,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// status a sequence gets when one of its barriers timed out (distinct from the reference's own failure, -1)
+#define ODO_STATUS_BARRIER_TIMEOUT (-2)
+
 struct GroupSync {
   double* partials;     // this sequence: [2][G][32]
   unsigned* counter;    // this sequence, zeroed before the launch
-  int* abort_flag;
+  int* abort_flag;      // this sequence, zeroed before the launch: one timed-out group does not touch the others
+  unsigned long long timeout_ns;
   unsigned target;      // barrier generation target (meaningful in thread 0)
   int parity;
   int G;
@@ -26,7 +30,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-// all CTAs of the group arrive, then proceed; the spin is bounded so a lost CTA cannot hang the device
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// All CTAs of the group arrive, then proceed.  The wait is bounded in TIME (globaltimer), not in polls: a CTA that
+// is merely late -- its SM busy with a concurrent kernel of another stream -- is waited for; a CTA that never comes
+// (the launch was not co-resident after all) ends the wait after timeout_ns, raises the flag of THIS sequence and
+// every CTA of the group leaves its barriers from then on.  The kernels report ODO_STATUS_BARRIER_TIMEOUT.
 __device__ __forceinline__ void group_barrier(GroupSync& gs) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -34,12 +47,16 @@ __device__ __forceinline__ void group_barrier(GroupSync& gs) {
     __threadfence();
     atomicAdd(gs.counter, 1u);
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     while (ld_acquire_u32(gs.counter) < gs.target) {
-      ++spins;
-      if ((spins & 1023u) == 0u && *(volatile int*)gs.abort_flag) break;
-      if (spins > (1u << 21)) {
-        atomicExch(gs.abort_flag, 1);
-        break;
+      if ((++spins & 255u) == 0u) {
+        if (*(volatile int*)gs.abort_flag) break;
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > gs.timeout_ns) {
+          atomicExch(gs.abort_flag, 1);
+          break;
+        }
       }
     }
     __threadfence();
@@ -97,11 +114,23 @@ __device__ __forceinline__ void group_allreduce(double* vals, double (*s_warp)[3
   }
   if (gs.G > 1) {
     group_barrier(gs);
+    // every CTA adds the G partials in the same fixed order, with the loads spread over the warps: warp w takes
+    // partials w, w + WARPS, ... (lane = value index), then the WARPS sub-sums are added in warp order.  (One thread
+    // per value walking all G partials costs G dependent L2 round trips: 9 us per LM iteration at G = 29.)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double s = 0.0;
+    if (lane < NV) {
+      const double* p = gs.partials + (int64_t)gs.parity * gs.G * 32 + lane;
+#pragma unroll 4
+      for (int c = wid; c < gs.G; c += WARPS) s += __ldcg(p + (int64_t)c * 32);
+    }
+    s_warp[wid][lane] = s;
+    __syncthreads();
     if (threadIdx.x < NV) {
-      double s = 0.0;
-      const double* p = gs.partials + (int64_t)gs.parity * gs.G * 32 + threadIdx.x;
-      for (int c = 0; c < gs.G; c++) s += __ldcg(p + (int64_t)c * 32);
-      s_tot[threadIdx.x] = s;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) t += s_warp[w][threadIdx.x];
+      s_tot[threadIdx.x] = t;
     }
     gs.parity ^= 1;
   }

@@ -6,7 +6,9 @@
 // host only uploads the n_seq stereo pairs and reads back the poses; the keyframe decision
 // (run_odometry_kitti_offline.cpp:254-270) is taken on the device.
 #include "common.cuh"
+#include "group_sync.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -133,6 +135,13 @@ __global__ void k_track_pose(SeqState* st, const LmResult* res, float* T_init, i
   if (b >= n) return;
   SeqState& s = st[b];
   if (s.dead) return;
+  if (res[b].status == ODO_STATUS_BARRIER_TIMEOUT) {
+    // the solve did not run to its end (group barrier timed out): no pose for this frame; the warm start and the
+    // poses of the last good frame stay (k_track_finalize reports the frame as -2)
+    s.lm_status = ODO_STATUS_BARRIER_TIMEOUT;
+    s.promote = 0;
+    return;
+  }
   const float* T = res[b].T;
   float Tinv[16];
   inverse4(T, Tinv);
@@ -156,6 +165,14 @@ __global__ void k_track_finalize(SeqState* st, const odo_depth_stats* ds, int* p
     promote_flags[b] = 0;
     s.promote = 0;
     s.status = -1;
+    return;
+  }
+  if (ds[b].status == ODO_STATUS_BARRIER_TIMEOUT || s.lm_status == ODO_STATUS_BARRIER_TIMEOUT) {
+    // a group barrier of k_refine / k_lm_solve timed out (group_sync.cuh): this frame has no result, but that is not
+    // the reference's `break` -- the sequence stays alive on its old keyframe and the caller sees status -2
+    s.promote = 0;
+    s.status = ODO_STATUS_BARRIER_TIMEOUT;
+    promote_flags[b] = 0;
     return;
   }
   if (ds[b].status != 0) {
@@ -213,6 +230,7 @@ struct odo_tracker {
   SeqState* h_state[2] = {nullptr, nullptr};  // pinned, one per ingest slot
   int G_lm = 1;
   int frame_id = 0;
+  bool broken = false;  // a launch failed half way: the queues were drained, the device state is undefined
   // stage boundaries of the last step (bench.py roofline): 0 start, 1 image pyramid, 2 LM solve + pose,
   // 3 blur + selection, 4 disparity search, 5 depth refinement, 6 depth pyramid + promotion + LM prepare
   cudaEvent_t ev[2][ODO_N_STAGES + 1] = {{nullptr}};
@@ -220,6 +238,14 @@ struct odo_tracker {
 };
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+// the launch helpers run on c->stream: a scope that points it at another stream and always points it back
+struct StreamScope {
+  odo_ctx* c;
+  cudaStream_t saved;
+  StreamScope(odo_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = saved; }
+};
 
 // queues all kernels of one frame (one frame per sequence) on the compute stream; no host wait
 // R8: the raw right frames as u8 when the caller already has them on the device (u8 ingest), else nullptr
@@ -242,21 +268,21 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   t->lm_ran[slot] = !first;
   if (!first) {
     // Solve against the keyframe (:215), forked onto the LM stream
-    cudaStream_t main_stream = c->stream;
-    cudaEventRecord(t->ev_fork, main_stream);
+    cudaEventRecord(t->ev_fork, c->stream);
     cudaStreamWaitEvent(t->lm_stream, t->ev_fork, 0);
-    c->stream = t->lm_stream;
-    cudaEventRecord(t->ev_lm[slot][0], t->lm_stream);
-    launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, QuantOut(), PYR_UPPER_LEVELS);
-    const int rc = launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n,
-                                   t->G_lm, -1);
-    if (rc == 0) {
-      k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
-      c->launches++;
+    int rc;
+    {
+      StreamScope on_lm(c, t->lm_stream);
+      cudaEventRecord(t->ev_lm[slot][0], t->lm_stream);
+      launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, QuantOut(), PYR_UPPER_LEVELS);
+      rc = launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1);
+      if (rc == 0) {
+        k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
+        c->launches++;
+      }
+      cudaEventRecord(t->ev_lm[slot][1], t->lm_stream);
+      cudaEventRecord(t->ev_lm_done, t->lm_stream);
     }
-    cudaEventRecord(t->ev_lm[slot][1], t->lm_stream);
-    cudaEventRecord(t->ev_lm_done, t->lm_stream);
-    c->stream = main_stream;
     if (rc != 0) return -1;
   }
   cudaEventRecord(ev[2], c->stream);
@@ -267,6 +293,7 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
   cudaEventRecord(ev[4], c->stream);
   t->dw.rawR8 = R8;
   t->dw.rawR8_stride = t->npx;
+  t->dw.busy_sms = first ? 0 : std::min(c->sm_count, t->G_lm * n);  // the LM solve of this frame may still be resident
   if (R8) cudaMemsetAsync(t->dw.raw_exact, 0xff, sizeof(int) * n, c->stream);  // u8 frames are exact by construction
   launch_depth_refine(c, L, R, in_stride, t->w, t->h, t->dp, t->dw, n);
   cudaEventRecord(ev[5], c->stream);
@@ -296,7 +323,10 @@ static int tracker_launch(odo_tracker* t, const float* L, const float* R, int sl
 static int tracker_finish(odo_tracker* t, int slot, float* pose_abs, float* pose_kf, int* is_keyframe, int* status) {
   odo_ctx* c = t->c;
   const int n = t->n;
-  ODO_CUDA_OK(c, cudaEventSynchronize(t->ev_done[slot]));
+  if (cudaEventSynchronize(t->ev_done[slot]) != cudaSuccess) {
+    c->err = "tracker: waiting for the frame failed";
+    return -2;
+  }
   for (int i = 0; i < ODO_N_STAGES; i++) cudaEventElapsedTime(&t->stage_ms[i], t->ev[slot][i], t->ev[slot][i + 1]);
   // the solve runs on its own stream, concurrently with stages 2-4
   if (t->lm_ran[slot]) cudaEventElapsedTime(&t->stage_ms[1], t->ev_lm[slot][0], t->ev_lm[slot][1]);
@@ -312,10 +342,28 @@ static int tracker_finish(odo_tracker* t, int slot, float* pose_abs, float* pose
   return rc;
 }
 
+// a launch failed after copies / kernels of the frame were already queued: drain everything so that no queued work
+// still reads the ingest slots, and refuse further frames (the device-side state is no longer consistent)
+static int tracker_break(odo_tracker* t) {
+  const std::string why = t->c->err;
+  cudaStreamSynchronize(t->copy_stream);
+  cudaStreamSynchronize(t->lm_stream);
+  cudaStreamSynchronize(t->c->stream);
+  t->broken = true;
+  t->c->err = "tracker: launch failed, tracker is unusable (" + why + ")";
+  return -1;
+}
+
+static bool tracker_usable(odo_tracker* t) {
+  if (t && !t->broken) return true;
+  if (t) t->c->err = "tracker: unusable after a failed launch";
+  return false;
+}
+
 // starts the host->device copies of one frame on the copy stream and queues the frame behind them
 template <typename T>
 static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const* right) {
-  if (!t || !left || !right) return -1;
+  if (!tracker_usable(t) || !left || !right) return -1;
   odo_ctx* c = t->c;
   ODO_CUDA_OK(c, cudaSetDevice(c->device));
   if (t->n_enqueued - t->n_collected >= 2) {
@@ -341,7 +389,7 @@ static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const*
     launch_u8_to_f32(c, t->in_u8[slot] + (size_t)t->n * t->npx, t->in_right[slot], t->npx * t->n);
   }
   if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, u8 ? t->in_u8[slot] + (size_t)t->n * t->npx : nullptr) != 0)
-    return -1;
+    return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
@@ -430,21 +478,30 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
     return -1;
   }
   t->h_state[1] = t->h_state[0] + n_seq;
-  cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&t->lm_stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming);
+  cudaError_t ce = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
+  auto ok = [&ce](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
+  ok(cudaStreamCreateWithFlags(&t->lm_stream, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  ok(cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming));
   for (int k = 0; k < 2; k++)
-    for (int i = 0; i < 2; i++) cudaEventCreate(&t->ev_lm[k][i]);
+    for (int i = 0; i < 2; i++) ok(cudaEventCreate(&t->ev_lm[k][i]));
   for (int k = 0; k < 2; k++) {
-    for (int i = 0; i <= ODO_N_STAGES; i++) cudaEventCreate(&t->ev[k][i]);
-    cudaEventCreateWithFlags(&t->ev_copied[k], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&t->ev_consumed[k], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming);
+    for (int i = 0; i <= ODO_N_STAGES; i++) ok(cudaEventCreate(&t->ev[k][i]));
+    ok(cudaEventCreateWithFlags(&t->ev_copied[k], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&t->ev_consumed[k], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming));
   }
-  k_track_init<<<(n_seq + 63) / 64, 64, 0, c->stream>>>(t->state, t->T_init, n_seq);
-  c->launches++;
-  ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (ce == cudaSuccess) {
+    k_track_init<<<(n_seq + 63) / 64, 64, 0, c->stream>>>(t->state, t->T_init, n_seq);
+    c->launches++;
+    ok(cudaGetLastError());
+    ok(cudaStreamSynchronize(c->stream));
+  }
+  if (ce != cudaSuccess) {
+    c->err = std::string("tracker: stream / event setup failed: ") + cudaGetErrorString(ce);
+    odo_tracker_destroy(t);
+    return -1;
+  }
   *out = t;
   return 0;
 }
@@ -517,8 +574,10 @@ int odo_tracker_collect(odo_tracker* t, float* pose_abs, float* pose_kf, int* is
     return -1;
   }
   const int slot = (int)(t->n_collected & 1);
+  const int rc = tracker_finish(t, slot, pose_abs, pose_kf, is_keyframe, status);
+  if (rc == -2) return tracker_break(t);  // the wait itself failed: the frame was NOT collected
   t->n_collected++;
-  return tracker_finish(t, slot, pose_abs, pose_kf, is_keyframe, status);
+  return rc;
 }
 
 int odo_tracker_step(odo_tracker* t, const float* const* left, const float* const* right, float* pose_abs,
@@ -563,7 +622,7 @@ int odo_tracker_set_rectify(odo_tracker* t, const odo_camera* left, const odo_ca
 }
 
 int odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, const uint8_t* const* right_raw) {
-  if (!t || !left_raw || !right_raw) return -1;
+  if (!tracker_usable(t) || !left_raw || !right_raw) return -1;
   odo_ctx* c = t->c;
   if (!t->in_raw[0]) {
     c->err = "tracker: odo_tracker_set_rectify has not run";
@@ -593,7 +652,7 @@ int odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, c
     c->err = "tracker: remap launch failed";
     return -1;
   }
-  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, R8) != 0) return -1;
+  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, R8) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
@@ -606,7 +665,7 @@ int odo_tracker_step_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, cons
 }
 
 int odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* right_dev) {
-  if (!t || !left_dev || !right_dev) return -1;
+  if (!tracker_usable(t) || !left_dev || !right_dev) return -1;
   odo_ctx* c = t->c;
   ODO_CUDA_OK(c, cudaSetDevice(c->device));
   if (t->n_enqueued - t->n_collected >= 2) {
@@ -614,7 +673,7 @@ int odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* 
     return -1;
   }
   const int slot = (int)(t->n_enqueued & 1);
-  if (tracker_launch(t, left_dev, right_dev, slot) != 0) return -1;
+  if (tracker_launch(t, left_dev, right_dev, slot) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
