@@ -263,17 +263,24 @@ static int lm_run(odo_ctx* c, const odo_pyr* i1, const odo_pyr* d1, const odo_py
   LmResult* res_dev = (LmResult*)(io + 256);
   ODO_CUDA_OK(c, cudaMemcpyAsync(T_dev, T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemsetAsync(res_dev, 0, sizeof(LmResult), c->stream));
+  const bool want_skip = (p->robust != 2 && lm_dense_enabled());
   const bool lists_cached = !lists_realloc && c->lists_img_id == i1->id && c->lists_dep_id == d1->id &&
+                            (c->lists_skip_dense == want_skip || !c->lists_skip_dense) &&
                             c->lists_K.fx == p->K.fx && c->lists_K.cx == p->K.cx && c->lists_K.cy == p->K.cy;
   if (!lists_cached) {
     // the cache ids are only valid for lists that were really built: cleared first, set after the launches succeeded
     c->lists_img_id = c->lists_dep_id = 0;
-    if (launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr) != 0) return -1;
+    if (launch_lm_prepare(c, i1->d, 0, d1->d, 0, g, p->K, L, 1, nullptr, 0, want_skip) != 0) return -1;
+    c->lists_skip_dense = want_skip;
     c->lists_img_id = i1->id;
     c->lists_dep_id = d1->id;
     c->lists_K = p->K;
   }
-  if (launch_lm_solve(c, L, i2->d, 0, g, *p, T_dev, res_dev, wk, 1, G, only_level) != 0) {
+  // dense levels are evaluated from the keyframe's own pyramids (8 B per pixel instead of a 48 B list entry)
+  LmDense dense;
+  dense.img1 = i1->d;
+  dense.dep = d1->d;
+  if (launch_lm_solve(c, L, i2->d, 0, g, *p, T_dev, res_dev, wk, 1, G, only_level, &dense) != 0) {
     c->lists_img_id = c->lists_dep_id = 0;
     return -1;
   }

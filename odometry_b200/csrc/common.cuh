@@ -25,6 +25,7 @@ struct odo_ctx {
   // the LM point lists in scratch were built from this (image, inverse-depth) pyramid pair: a caller that
   // solves several frames against one keyframe (run_odometry_kitti_offline.cpp:215) pays for them once
   uint64_t lists_img_id = 0, lists_dep_id = 0;
+  bool lists_skip_dense = false;   // the cached lists lack the levels the dense evaluation covers
   odo_intrinsics lists_K = {0.f, 0.f, 0.f};
   // released pyramid buffers, reused by the next build of the same size (all work of a context is
   // ordered on its one stream, so reuse needs no synchronisation and no cudaMalloc per frame)
@@ -115,8 +116,10 @@ size_t lm_lists_bytes(const PyrGeom& g, int batch, LmLists* layout);  // fills o
 void lm_lists_bind(LmLists* L, void* mem, const PyrGeom& g, int batch);
 // dep_from_l0: dep_pyr holds only level 0 of each sequence's depth pyramid (levels 1.. are read through the
 // odd-pixel subsampling rule)
+// skip_dense: do not fill the lists of levels the solve will evaluate through LmDense (same density rule)
 int launch_lm_prepare(odo_ctx* c, const float* img_pyr, int64_t istride, const float* dep_pyr, int64_t dstride,
-                      const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active, int dep_from_l0 = 0);
+                      const PyrGeom& g, odo_intrinsics K, LmLists L, int batch, const int* active, int dep_from_l0 = 0,
+                      int skip_dense = 0);
 
 struct LmLevelOut {      // sums of the last evaluation at a level (test hook / stats)
   double H[21];
@@ -145,12 +148,22 @@ struct LmWork {          // device scratch of the solve kernel
 // wait bound of the group barriers in ns (env ODO_BARRIER_TIMEOUT_MS, default 2000 ms) and the test hook that makes
 // the last CTA of every group leave at once (env ODO_TEST_LOSE_CTA=1: the barrier-timeout path, tests only)
 unsigned long long group_timeout_ns();
+bool lm_dense_enabled();   // ODO_LM_DENSE=1: list-free evaluation of dense levels (LmDense)
 int group_test_lose_cta();
+// Dense levels (config 5: every interior pixel carries a depth) are evaluated straight from the keyframe's image and
+// inverse-depth pyramids -- 8 B per pixel instead of the 48 B list entry: the back-projection and the Jacobian are
+// recomputed per linearisation (lm.cu, eval_dense_level).  A level takes that path when the pointers are given and at
+// least half of its interior pixels are valid; the point list of such a level is not built.
+struct LmDense {
+  const float* img1 = nullptr;   // [batch][packed pyramid]
+  const float* dep = nullptr;    // [batch][packed pyramid] (all levels materialised)
+  int64_t istride = 0, dstride = 0;
+};
 // G = CTAs per sequence (1 .. sm_count).  only_level >= 0: evaluate that level once at exactly T_init
 // (test hook for odo_lm_linearize).
 int launch_lm_solve(odo_ctx* c, const LmLists& L, const float* img2_pyr, int64_t i2stride, const PyrGeom& g,
                     const odo_lm_params& p, const float* T_init_dev /*[batch][16]*/, LmResult* out_dev,
-                    LmWork wk, int batch, int G, int only_level);
+                    LmWork wk, int batch, int G, int only_level, const LmDense* dense = nullptr);
 size_t lm_work_bytes(const PyrGeom& g, int batch, int G);
 int lm_max_ctas(const odo_ctx* c);  // co-resident CTAs of the persistent solve kernel on this device
 void lm_work_bind(LmWork* w, void* mem, const PyrGeom& g, int batch, int G);

@@ -230,6 +230,162 @@ __global__ void __launch_bounds__(32 * kSelWarpsPerCta) k_select_warp(int W, int
   }
 }
 
+// Second generation of the one-warp-per-block selection (default).  Same results bit for bit, three changes:
+//  * the block's pixels plus a one-pixel halo are staged in shared memory with coalesced loads -- (bw + 2)(bh + 2)
+//    = 1000 loads per block instead of 4 x 874 scattered ones (the first version spent half of its stall samples
+//    waiting for the gradient loads);
+//  * everything works on the SQUARED magnitude v = gx^2 + gy^2: sqrt is monotone, so the k-th smallest magnitude
+//    is the sqrt of the k-th smallest v (:324), and `magnitude > th` (:330) is `v >= tv` with tv the smallest float
+//    whose correctly rounded sqrt exceeds th -- computed once per block in fp64 from the midpoint between th and the
+//    next float (the midpoint's square is never a float, so there is no tie); 874 sqrt per block become one;
+//  * once the bit-by-bit search has narrowed the k-th smallest down to <= 32 candidates, they are compacted to one
+//    per lane and the remaining rounds cost one compare + ballot instead of NPL compares + REDUX.
+template <int NPL>
+__global__ void __launch_bounds__(32 * kSelWarpsPerCta, 5) k_select_tile(int W, int H, odo_depth_params p, DepthWork d,
+                                                                      int tile_stride) {
+  extern __shared__ float s_tile[];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int block_id = blockIdx.x * kSelWarpsPerCta + wic;
+  const int b = blockIdx.y;
+  if (block_id >= kGridBlocks) return;
+  const int64_t npx = (int64_t)W * H;
+  const float* bl = d.blurL + b * d.blurL_stride;
+  uint8_t* val = d.val + b * npx;
+  const int bw = (W - p.boundary * 2) / 32, bh = (H - p.boundary * 2) / 16;
+  const int start_y = p.boundary + (block_id / 32) * bh;
+  const int start_x = p.boundary + (block_id % 32) * bw;
+  const int n = bw * bh;
+  const int tw = bw + 2, tn = tw * (bh + 2);
+  float* tile = s_tile + wic * tile_stride;
+  {
+    const float* src = bl + (int64_t)(start_y - 1) * W + (start_x - 1);
+    const int dc = 32 % tw, dr = 32 / tw;
+    int c = lane % tw, r = lane / tw;
+    for (int i = lane; i < tn; i += 32) {
+      tile[i] = __ldg(src + (int64_t)r * W + c);
+      c += dc;
+      r += dr;
+      if (c >= tw) { c -= tw; r++; }
+    }
+  }
+  __syncwarp();
+  const int dx = 32 % bw, dy = 32 / bw;  // pixel i + 32 from pixel i inside the block
+  unsigned v[NPL];
+  {
+    int x = lane % bw, y = lane / bw;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) {
+      // 0xffffffff (a NaN pattern): never below a candidate threshold, never at or above the block threshold
+      unsigned u = 0xffffffffu;
+      if (j * 32 + lane < n) {
+        const float* t = tile + (y + 1) * tw + (x + 1);
+        const float gx = __fmul_rn(0.5f, __fsub_rn(t[1], t[-1]));      // :315-317 on the blurred left image
+        const float gy = __fmul_rn(0.5f, __fsub_rn(t[tw], t[-tw]));
+        u = __float_as_uint(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+      }
+      v[j] = u;
+      x += dx;
+      y += dy;
+      if (x >= bw) { x -= bw; y++; }
+    }
+  }
+  __syncwarp();  // the tile is free from here on: its first 32 words serve the compaction below
+  // k-th smallest v, k = n / 2 (block_grad[n / 2] after std::nth_element, :324): v >= +0, bit patterns order like values
+  const int k = n / 2;
+  unsigned ans = 0u;
+  int below_lo = 0, below_hi = n;  // #{v < ans} and #{v < ans + 2^(bit+1)}: the k-th smallest lies in between
+  int bit = 30;
+#pragma unroll 1
+  for (; bit >= 0; bit--) {
+    if (below_hi - below_lo <= 32) break;
+    const unsigned cand = ans | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) cnt += (v[j] < cand) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt <= k) {
+      ans = cand;
+      below_lo = cnt;
+    } else {
+      below_hi = cnt;
+    }
+  }
+  if (bit >= 0) {
+    // the candidates left, ans <= v < ans + 2^(bit+1) (all of them when bit == 30), one per lane
+    const unsigned hi = (bit == 30) ? 0x80000000u : ans + (2u << bit);
+    unsigned* s_c = reinterpret_cast<unsigned*>(tile);
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) mine += (v[j] >= ans && v[j] < hi) ? 1 : 0;
+    int pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    int pos = pre - mine;
+#pragma unroll
+    for (int j = 0; j < NPL; j++)
+      if (v[j] >= ans && v[j] < hi) s_c[pos++] = v[j];
+    __syncwarp();
+    const int nc = below_hi - below_lo;
+    const unsigned cv = (lane < nc) ? s_c[lane] : 0xffffffffu;
+    const int kk = k - below_lo;  // rank of the wanted value among the candidates
+    int lo = 0;
+#pragma unroll 1
+    for (; bit >= 0; bit--) {
+      const unsigned cand = ans | (1u << bit);
+      const int cnt = lo + __popc(__ballot_sync(0xffffffffu, cv >= ans && cv < cand));
+      if (cnt <= kk) {
+        ans = cand;
+        lo = cnt;
+      }
+    }
+  }
+  const float med = __fsqrt_rn(__uint_as_float(ans));
+  const float block_th = __fadd_rn(med, p.grad_th);  // :325
+  // sqrt_rn(v) > th  <=>  v >= tv
+  float tv;
+  if (block_th >= 0.0f && block_th < 3.0e38f) {
+    const float nx = __uint_as_float(__float_as_uint(block_th) + 1u);
+    const double mid = 0.5 * ((double)block_th + (double)nx);
+    tv = __double2float_ru(mid * mid);
+  } else if (block_th < 0.0f) {
+    tv = 0.0f;                       // every magnitude (>= 0) is above a negative threshold
+  } else {
+    tv = __uint_as_float(0x7fc00000u);  // NaN / huge threshold: nothing is above it
+  }
+  // first <= 80 pixels with magnitude > th in raster order, :327-341
+  int* sel = d.sel_xy + ((int64_t)b * kGridBlocks + block_id) * kSelMax;
+  int run = 0;
+  {
+    int x = lane % bw, y = lane / bw;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) {
+      if (run < kSelMax) {  // warp uniform
+        const bool f = __uint_as_float(v[j]) >= tv;   // false for the NaN pattern of absent pixels
+        const unsigned mk = __ballot_sync(0xffffffffu, f);
+        const int rank = run + __popc(mk & ((1u << lane) - 1u));
+        if (f && rank < kSelMax) {
+          val[(int64_t)(start_y + y) * W + start_x + x] = 1;
+          sel[rank] = ((start_y + y) << 16) | (start_x + x);
+        }
+        run += __popc(mk);
+      }
+      x += dx;
+      y += dy;
+      if (x >= bw) { x -= bw; y++; }
+    }
+  }
+  const int cnt = min(run, kSelMax);
+  for (int t = lane; t < kSelMax; t += 32)
+    if (t >= cnt) sel[t] = -1;  // unfilled slots of this block's list
+  if (lane == 0) {
+    d.sel_count[b * kGridBlocks + block_id] = cnt;
+    atomicAdd(&d.stats[b].n_selected, cnt);
+  }
+}
+
 // ---- disparity line search ----------------------------------------------------------------------------
 // Work item = one image row of one sequence.  The CTA compacts the row of the validity mask into an
 // ascending list of selected columns, stages the five right rows y-2..y+2 it needs in shared memory
@@ -333,13 +489,35 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   // ---- selected columns of this row, ascending: "if (*(left_val_row_ptr+x) == 0) continue", :352 ----
+  // 16 mask bytes per thread (one aligned 16-byte load), so a KITTI row is compacted in ONE ballot-free round: per
+  // thread the non-zero bytes become a bit mask, a warp scan and four warp totals give the write position.
   const uint8_t* vrow = d.val + b * npx + (int64_t)y * W;
+  const int mis = (int)(reinterpret_cast<uintptr_t>(vrow) & 15);
+  const uint4* vq = reinterpret_cast<const uint4*>(vrow - mis);   // the bytes in front of / behind the row belong to the same plane
+  const int nchunk = (mis + W + 15) >> 4;
   int n = 0;
-  for (int x0 = bnd; x0 < W - bnd; x0 += kDispThreads) {
-    const int x = x0 + threadIdx.x;
-    const bool f = (x < W - bnd) && (__ldg(vrow + x) != 0);
-    const unsigned mk = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_w[wid] = __popc(mk);
+  for (int j0 = 0; j0 < nchunk; j0 += kDispThreads) {
+    const int j = j0 + threadIdx.x;
+    unsigned m16 = 0u;
+    const int c0 = j * 16 - mis;   // image column of byte 0 of this thread's chunk
+    if (j < nchunk) {
+      const uint4 q = __ldg(vq + j);
+      auto nz4 = [](unsigned w) -> unsigned {   // bit k = byte k of w is non-zero
+        const unsigned hb = ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu | w) & 0x80808080u;
+        return ((hb >> 7) * 0x01020408u) >> 24;
+      };
+      m16 = nz4(q.x) | (nz4(q.y) << 4) | (nz4(q.z) << 8) | (nz4(q.w) << 12);
+      const int lo = max(bnd - c0, 0), hi = min(W - bnd - c0, 16);   // columns [bnd, W - bnd) only
+      m16 = (hi > lo) ? (m16 & ((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+    }
+    const int cnt = __popc(m16);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
     int woff = 0, tot = 0;
 #pragma unroll
@@ -347,7 +525,11 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
       if (k < wid) woff += s_w[k];
       tot += s_w[k];
     }
-    if (f) s_xs[n + woff + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)x;
+    int pos = n + woff + inc - cnt;
+    while (m16) {
+      s_xs[pos++] = (uint16_t)(c0 + __ffs(m16) - 1);
+      m16 &= m16 - 1u;
+    }
     n += tot;
     __syncthreads();
   }
@@ -525,6 +707,29 @@ __global__ void __launch_bounds__(kDispThreads, QPATH ? 6 : 4) k_disparity(int W
         refresh();
         // chunks entirely left of every pixel of the group and entirely right of the border: no range test, pruned
         const uint4* q_p = s_rec + (base - lane);
+        // two chunks per trip: both records are in flight together; a chunk the bound could not reject is evaluated
+        // before the next one is looked at, so `best` still moves in scan order (a threshold computed a chunk early is
+        // only looser, never wrong)
+        for (; base - 63 >= bnd; base -= 64, q_p -= 64) {
+          const uint4 pk0 = q_p[0], pk1 = q_p[-32];
+          bool lv0 = false, lv1 = false;
+#pragma unroll
+          for (int i = 0; i < kDispP; i++) {
+            const int a0 = (int)__dp4a(lb8[i], pk0.y, __dp4a(la8[i], pk0.x, pk0.z));
+            const int a1 = (int)__dp4a(lb8[i], pk1.y, __dp4a(la8[i], pk1.x, pk1.z));
+            lv0 |= a0 >= thr[i];
+            lv1 |= a1 >= thr[i];
+          }
+          const bool s0 = __any_sync(0xffffffffu, lv0), s1 = __any_sync(0xffffffffu, lv1);
+          if (s0) {
+            const bool up = full_chunk(base, false);
+            if (__any_sync(0xffffffffu, up)) refresh();
+          }
+          if (s1) {
+            const bool up = full_chunk(base - 32, false);
+            if (__any_sync(0xffffffffu, up)) refresh();
+          }
+        }
         for (; base - 31 >= bnd; base -= 32, q_p -= 32) {
           const uint4 pk = q_p[0];
           const int ne8 = (int)pk.z;
@@ -1139,9 +1344,15 @@ void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, i
     c->launches++;
   }
   const int bn = ((w - 2 * p.boundary) / 32) * ((h - 2 * p.boundary) / 16);
-  if (bn <= 32 * 28 && !std::getenv("ODO_SELECT_CTA"))
-    k_select_warp<28><<<dim3(kGridBlocks / kSelWarpsPerCta, batch), 32 * kSelWarpsPerCta, 0, c->stream>>>(w, h, p, d);
-  else
+  if (bn <= 32 * 28 && !std::getenv("ODO_SELECT_CTA")) {
+    const int bw = (w - 2 * p.boundary) / 32, bh = (h - 2 * p.boundary) / 16;
+    const int tile_stride = ((bw + 2) * (bh + 2) + 31) & ~31;
+    if (std::getenv("ODO_SELECT_V1"))   // first generation (A/B switch)
+      k_select_warp<28><<<dim3(kGridBlocks / kSelWarpsPerCta, batch), 32 * kSelWarpsPerCta, 0, c->stream>>>(w, h, p, d);
+    else
+      k_select_tile<28><<<dim3(kGridBlocks / kSelWarpsPerCta, batch), 32 * kSelWarpsPerCta,
+                          sizeof(float) * tile_stride * kSelWarpsPerCta, c->stream>>>(w, h, p, d, tile_stride);
+  } else
     k_select<<<dim3(kGridBlocks, batch), kSelThreads, 0, c->stream>>>(w, h, p, d);
   c->launches++;
 }
@@ -1211,11 +1422,14 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
   const int gmax = (d.cap + kRefThreads - 1) / kRefThreads;  // one slot per thread
   // G CTAs per sequence, all co-resident (group barrier).  Fewer CTAs per sequence mean more slots, hence more shared
   // memory, per CTA, which can lower the occupancy again: settle from the register-limited value downwards.
-  // SMs this launch can count on: all of them, minus the ones a concurrently running persistent kernel holds -- but only
-  // while that still leaves the refinement most of the device; a large batch keeps the whole-device sizing (its LM
-  // solve has finished by the time the refinement starts, and fewer CTAs per sequence would only slow the passes)
+  // SMs this launch can count on: all of them, minus the ones a concurrently running persistent kernel holds -- for
+  // small batches only.  There the LM solve (a latency chain of the same length whatever the batch) outlasts the depth
+  // pipeline, and a refinement sized for the whole device would sit in the queue until the solve has drained (measured
+  // at 8 sequences: 0.64 -> 0.14 ms).  A large batch keeps the whole-device sizing: its solve has finished by the time
+  // the refinement starts, and fewer CTAs per sequence would only slow the passes (and push the slot state out of
+  // shared memory).
   int free_sms = c->sm_count;
-  if (d.busy_sms > 0 && d.busy_sms * 2 <= c->sm_count + 2 && !std::getenv("ODO_REFINE_WHOLE_DEVICE")) free_sms -= d.busy_sms;
+  if (d.busy_sms > 0 && d.busy_sms < c->sm_count && batch <= 40 && !std::getenv("ODO_REFINE_WHOLE_DEVICE")) free_sms -= d.busy_sms;
   int G = gmax;
   if (const char* e = std::getenv("ODO_REFINE_CTAS_PER_SEQ")) {  // test / experiment knob
     const int g = std::atoi(e);

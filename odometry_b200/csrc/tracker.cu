@@ -799,7 +799,8 @@ int odo_depth_optimize(odo_ctx* c, const float* left, const float* right, int w,
   ODO_CUDA_OK(c, cudaMemcpyAsync(&hs, dw.stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   if (st) *st = hs;
-  return hs.status;
+  if (hs.status == ODO_STATUS_BARRIER_TIMEOUT) c->err = "depth_optimize: group barrier timed out (CTAs not co-resident?)";
+  return hs.status == 0 ? 0 : -1;
 }
 
 int odo_compute_depth(odo_ctx* c, const float* left, const float* right, int w, int h, const odo_depth_params* p,
@@ -821,9 +822,11 @@ int odo_compute_depth(odo_ctx* c, const float* left, const float* right, int w, 
   if (dep) ODO_CUDA_OK(c, cudaMemcpyAsync(dep, dw.dep, npx * 4, cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaMemcpyAsync(&hs, dw.stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  if (st) *st = hs;
-  if (hs.status != 0) c->err = "Depth optimization failed!";
-  return hs.status;
+  if (st) *st = hs;   // status -1: the reference's own failure (< 500 valid); -2: a group barrier of k_refine timed out
+  if (hs.status != 0)
+    c->err = (hs.status == ODO_STATUS_BARRIER_TIMEOUT) ? "compute_depth: group barrier timed out (CTAs not co-resident?)"
+                                                       : "Depth optimization failed!";
+  return hs.status == 0 ? 0 : -1;
 }
 
 }  // extern "C"

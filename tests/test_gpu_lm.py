@@ -144,10 +144,13 @@ def test_mismatched_pyramids_rejected(ctx, scene):
     assert rc == -1
 
 
-def test_dense_4k_linearize(ctx):
-    """Config 5 shape: 3840x2160, dense depth, level 0 and the coarsest level of a 6-level pyramid."""
+@pytest.mark.parametrize("dense_path", [False, True])
+def test_dense_4k_linearize(ctx, dense_path, monkeypatch):
+    """Config 5 shape: 3840x2160, dense depth, level 0 and the coarsest level of a 6-level pyramid; through the point
+    list (default) and through the list-free evaluation of dense levels (ODO_LM_DENSE=1)."""
     import torch
     from odometry_b200 import synth
+    monkeypatch.setenv("ODO_LM_DENSE", "1" if dense_path else "0")
     sc = synth.make_scene(5, 2)
     s = 3840 / 1241.0
     kw = dict(w=3840, h=2160, device="cuda", fx=synth.FX * s, cx=synth.CX * s, cy=synth.CY * s)
@@ -168,27 +171,42 @@ def test_dense_4k_linearize(ctx):
         assert rel_err(got["g"], wide["g"]) < 1e-9
 
 
-def test_dense_4k_solve_matches_oracle(ctx):
+_CASE_4K = {}
+
+
+def _case_4k():
+    """frames, oracle pyramids and the oracle's Solve of the config-5 parity case (computed once: ~25 s of CPU)"""
+    if not _CASE_4K:
+        from odometry_b200 import synth
+        sc = synth.make_scene(1000, 2)
+        kw = dict(w=3840, h=2160, device="cuda", fx=synth.FX, cx=synth.CX, cy=synth.CY)   # the reference's hard-coded camera
+        T1 = synth.pose_from_motion()
+        T2 = synth.pose_from_motion(0.0, 0.0, 0.06, 0.0, math.radians(0.03), 0.0)
+        L1, z1 = synth.render(sc, T1, **kw)
+        L2, _ = synth.render(sc, T2, **kw)
+        L1, L2 = L1.cpu().numpy().astype(np.float32), L2.cpu().numpy().astype(np.float32)
+        dep = (1.0 / z1.cpu().numpy()).astype(np.float32)
+        iters = (10, 20, 30, 30, 30, 30)
+        orc, oT, ost = oracle.lm_solve(oracle.image_pyramid(L1, 6, True, packed=True), oracle.depth_pyramid(dep, 6, False, packed=True),
+                                       oracle.image_pyramid(L2, 6, True, packed=True), 3840, 2160, 6, oracle.lm_params(max_iters=iters))
+        _CASE_4K.update(L1=L1, L2=L2, dep=dep, iters=iters, orc=orc, oT=oT, ost=ost, gt=synth.relative_pose(T1, T2).astype(np.float32))
+    return _CASE_4K
+
+
+@pytest.mark.parametrize("dense_path", [False, True])
+def test_dense_4k_solve_matches_oracle(ctx, dense_path, monkeypatch):
     """Config 5: one 3840x2160 frame, 6-level pyramids, all-pixel dense alignment -- the whole coarse-to-fine Solve
-    (src/lm_optimizer.cpp:73-160, iters {10,20,30,30,30,30}) against the oracle in ORC_SUM_WIDE."""
-    from odometry_b200 import synth
-    sc = synth.make_scene(1000, 2)
-    kw = dict(w=3840, h=2160, device="cuda", fx=synth.FX, cx=synth.CX, cy=synth.CY)   # the reference's hard-coded camera
-    T1 = synth.pose_from_motion()
-    T2 = synth.pose_from_motion(0.0, 0.0, 0.06, 0.0, math.radians(0.03), 0.0)
-    L1, z1 = synth.render(sc, T1, **kw)
-    L2, _ = synth.render(sc, T2, **kw)
-    L1, L2 = L1.cpu().numpy().astype(np.float32), L2.cpu().numpy().astype(np.float32)
-    dep = (1.0 / z1.cpu().numpy()).astype(np.float32)
-    iters = (10, 20, 30, 30, 30, 30)
-    p1, d1, p2 = ctx.image_pyramid(L1, 6, True), ctx.depth_pyramid(dep, 6, False), ctx.image_pyramid(L2, 6, True)
-    rc, T, st = ctx.lm_solve(p1, d1, p2, capi.default_lm_params(max_iters=iters))
-    orc, oT, ost = oracle.lm_solve(oracle.image_pyramid(L1, 6, True, packed=True), oracle.depth_pyramid(dep, 6, False, packed=True),
-                                   oracle.image_pyramid(L2, 6, True, packed=True), 3840, 2160, 6, oracle.lm_params(max_iters=iters))
-    assert rc == orc == 0
-    assert list(st.iters)[:6] == list(ost.iters)[:6] and list(st.n_res)[:6] == list(ost.n_res)[:6]
-    ang, tr = pose_err(T, oT)
+    (src/lm_optimizer.cpp:73-160, iters {10,20,30,30,30,30}) against the oracle in ORC_SUM_WIDE, on both evaluation paths
+    (point list; list-free evaluation of dense levels, ODO_LM_DENSE=1)."""
+    monkeypatch.setenv("ODO_LM_DENSE", "1" if dense_path else "0")
+    c = _case_4k()
+    p1, d1, p2 = ctx.image_pyramid(c["L1"], 6, True), ctx.depth_pyramid(c["dep"], 6, False), ctx.image_pyramid(c["L2"], 6, True)
+    rc, T, st = ctx.lm_solve(p1, d1, p2, capi.default_lm_params(max_iters=c["iters"]))
+    assert rc == c["orc"] == 0
+    assert list(st.iters)[:6] == list(c["ost"].iters)[:6] and list(st.n_res)[:6] == list(c["ost"].n_res)[:6]
+    ang, tr = pose_err(T, c["oT"])
     assert ang < 1e-4 and tr < 1e-4, (ang, tr)
-    gt = synth.relative_pose(T1, T2).astype(np.float32)
-    ang, tr = pose_err(T, gt)
+    ang, tr = pose_err(T, c["gt"])
     assert tr < 5e-3 and ang < 1e-3, (ang, tr)
+    for p in (p1, d1, p2):
+        p.release()
