@@ -8,7 +8,7 @@ the per-frame body of run_odometry_kitti_offline.cpp:198-271).  With --gpus N ev
 own S sequences (sharding of independent sequences, no data-path collective => weak scaling);
 --seqs-total T shards T sequences over the ranks instead (config 4 as written: strong scaling).
 
-  value : frames/s with the step's inputs already resident in HBM (odo_tracker_enqueue_dev)
+  value : frames/s with the step's inputs (u8 frames) already resident in HBM (odo_tracker_enqueue_dev_u8)
   e2e   : frames/s through the reference-facing C-ABI call with HOST buffers: u8 images in pinned
           memory (what the reference's imread leaves, run_odometry_kitti_offline.cpp:334-359), H2D of
           the step's frames and D2H of the poses inside the timed region; the CV_32F variant of the
@@ -867,15 +867,13 @@ def run_kitti(args, rank, local_rank, world):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---------------- leg 1: inputs resident in HBM ----------------
-    frames_f32 = frames_u8.to(torch.float32)                            # [F][S][2][H][W] float32 on device
-    left_dev = frames_f32[:, :, 0].contiguous()
-    right_dev = frames_f32[:, :, 1].contiguous()
-    del frames_f32
+    # ---------------- leg 1: inputs resident in HBM (CV_8U, the reference's input format) ----------------
+    left_dev = frames_u8[:, :, 0].contiguous()                          # [F][S][H][W] u8 on device
+    right_dev = frames_u8[:, :, 1].contiguous()
     trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
 
     def enq_dev(t, i, f):
-        t.enqueue_dev(left_dev[f, i * St].data_ptr(), right_dev[f, i * St].data_ptr())
+        t.enqueue_dev(left_dev[f, i * St].data_ptr(), right_dev[f, i * St].data_ptr(), u8=True)
 
     run_pipelined(trks, enq_dev, 0, 1 + Wm)
     sampler = ClockSampler(local_rank)
@@ -914,10 +912,16 @@ def run_kitti(args, rank, local_rank, world):
     if not args.no_e2e:
         def e2e_leg(host, u8):
             trks = [capi.Tracker(c, W, H, LEVELS, St) for c in ctxs]
+            # one host pointer per image, as a C++ caller holds them (cv::Mat::data of every frame): the arrays are built
+            # once, outside the timed region -- indexing a torch tensor 128 times per step costs more than the GPU step
+            esz = host.element_size()
+            p0 = host.data_ptr()
+            arrs = [[(t.pointer_array([p0 + esz * (((f * S + i * St + s) * 2 + 0) * H * W) for s in range(St)]),
+                      t.pointer_array([p0 + esz * (((f * S + i * St + s) * 2 + 1) * H * W) for s in range(St)]))
+                     for i, t in enumerate(trks)] for f in range(n_frames)]
 
             def enq_host(t, i, f):
-                base = host[f, i * St:(i + 1) * St]
-                t.enqueue_ptrs([base[s, 0].data_ptr() for s in range(St)], [base[s, 1].data_ptr() for s in range(St)], u8=u8)
+                t.enqueue_arrays(arrs[f][i][0], arrs[f][i][1], u8=u8)
 
             run_pipelined(trks, enq_host, 0, 1 + Wm)
             ms = timed(lambda: run_pipelined(trks, enq_host, 1 + Wm, n_frames))
@@ -957,8 +961,8 @@ def run_kitti(args, rank, local_rank, world):
     pyr_px = sum((W >> l) * (H >> l) for l in range(LEVELS))
     # algorithmic (compulsory) bytes per frame of each stage, DESIGN.md section 3
     alg_bytes = {
-        "image_pyramid": 4 * (npx + pyr_px),
-        "blur_select": 8 * npx + 4 * npx + npx,              # blur R (read + write), gradient read of blur L, val
+        "image_pyramid": npx + 4 * pyr_px,                   # u8 frame in, float levels out
+        "blur_select": 5 * npx + 4 * npx + npx,              # blur R (u8 read, float write), gradient read of blur L, val
         "disparity": 17 * npx,                               # read L,R blur, val; write disp, dep
         "depth_refine": 20 * 40960,                          # one pass of the slot state (11-15 passes run)
         "depth_pyr_promote_prepare": 8 * pyr_px,             # point lists of a promoted keyframe: read img + depth
@@ -1014,18 +1018,18 @@ def run_kitti(args, rank, local_rank, world):
     cfg5 = None
     if not args.no_extras:
         trk1 = capi.Tracker(ctx, W, H, LEVELS, 1)
-        l1 = frames_u8[:, 0, 0].to(torch.float32).contiguous()
-        r1 = frames_u8[:, 0, 1].to(torch.float32).contiguous()
+        l1 = frames_u8[:, 0, 0].contiguous()
+        r1 = frames_u8[:, 0, 1].contiguous()
         for f in range(0, 1 + Wm):
-            assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr())[0] == 0
+            assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr(), u8=True)[0] == 0
 
         def lat():
             for f in range(1 + Wm, n_frames):
-                assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr())[0] == 0     # one frame at a time: enqueue + collect
+                assert trk1.step_dev(l1[f].data_ptr(), r1[f].data_ptr(), u8=True)[0] == 0     # one frame at a time: enqueue + collect
 
         ms_lat = timed(lat)
         latency = {"latency_s1_ms": ms_lat / K, "frames": K,
-                   "what": "one 1241x376 stereo frame of ONE sequence, step by step (odo_tracker_step_dev: the pose is read back "
+                   "what": "one 1241x376 stereo frame of ONE sequence, step by step (odo_tracker_step_dev_u8: the pose is read back "
                            "before the next frame is queued): pyramid + Solve + ComputeDepth + keyframe rule"}
         trk1.close()
         del l1, r1

@@ -11,6 +11,9 @@
  *   - 4x4 poses: float[16] COLUMN-MAJOR (Affine4f = Eigen::Matrix<float,4,4>, include/data_types.h:24).
  *   - status: int, 0 = success, -1 = failure (GlobalStatus / OptimizerStatus, include/data_types.h:27-28);
  *     nothing aborts or throws; odo_last_error() returns the message the reference would have printed.
+ *     The statistics structs and the tracker's per-sequence status additionally use -2 for "a group barrier of a
+ *     persistent kernel timed out" (a launch that could not be made co-resident): the call still returns -1, but
+ *     this is not the reference's own failure and does not end a tracked sequence.
  *   - a context owns one CUDA stream; calls on one context are serialised, contexts are independent
  *     (the reference objects are single-threaded).
  */
@@ -220,6 +223,12 @@ int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* ri
                           float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 /* same without waiting (pair with odo_tracker_collect); the device buffers must stay untouched until then */
 int  odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* right_dev);
+/* the same two for CV_8U frames resident on the device ([n_seq][h][w] bytes per eye), the format imread(GRAYSCALE)
+ * produces (run_odometry_kitti_offline.cpp:342-347): the convertTo(CV_32F) of :348,358 happens on load inside the
+ * kernels that read the raw frame (blur, pyrDown, depth refinement); results are identical to the float entry points */
+int  odo_tracker_step_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint8_t* right_dev,
+                             float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
+int  odo_tracker_enqueue_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint8_t* right_dev);
 
 /* device time of the stages of the last step, in ms (CUDA events on the context's stream):
  * 0 image pyramid, 1 LM solve + pose update, 2 blur + selection, 3 disparity search,

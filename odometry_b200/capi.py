@@ -54,6 +54,7 @@ EXPORTS = [
     "odo_lm_solve", "odo_lm_linearize", "odo_tracker_create", "odo_tracker_destroy",
     "odo_tracker_step", "odo_tracker_step_u8", "odo_tracker_step_dev", "odo_tracker_stage_ms",
     "odo_tracker_enqueue", "odo_tracker_enqueue_u8", "odo_tracker_enqueue_dev", "odo_tracker_collect",
+    "odo_tracker_step_dev_u8", "odo_tracker_enqueue_dev_u8",
     "odo_camera_create", "odo_camera_destroy", "odo_camera_configure", "odo_camera_set_maps", "odo_camera_levels",
     "odo_camera_intrinsics", "odo_camera_raw", "odo_camera_lm_intrinsics", "odo_camera_map_size",
     "odo_camera_maps_download", "odo_camera_undistort_rectify", "odo_camera_undistort_rectify_dev",
@@ -440,6 +441,16 @@ class Tracker:
         if fn(self.h, la, ra) != 0:
             raise OdoError(self.ctx.last_error())
 
+    def pointer_array(self, ptrs):
+        """a reusable C array of n_seq host addresses for enqueue_arrays (what a C++ caller holds anyway)"""
+        return (C.c_void_p * self.n)(*ptrs)
+
+    def enqueue_arrays(self, left_arr, right_arr, u8=False):
+        """enqueue_ptrs with pointer arrays built ahead of time (no per-frame Python work)"""
+        fn = lib().odo_tracker_enqueue_u8 if u8 else lib().odo_tracker_enqueue
+        if fn(self.h, left_arr, right_arr) != 0:
+            raise OdoError(self.ctx.last_error())
+
     def set_rectify(self, cam_left: "Camera", cam_right: "Camera", raw_w, raw_h):
         """Raw-camera ingest: later frames go through step_raw_u8 / enqueue_raw_ptrs as unrectified u8 images."""
         self._cams = (cam_left, cam_right)
@@ -459,8 +470,10 @@ class Tracker:
                                            *self._outs())
         return self._result(rc)
 
-    def enqueue_dev(self, left_dev_ptr, right_dev_ptr):
-        if lib().odo_tracker_enqueue_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr)) != 0:
+    def enqueue_dev(self, left_dev_ptr, right_dev_ptr, u8=False):
+        """frames resident on the device: [n_seq][h][w] float32 per eye, or uint8 with u8=True"""
+        fn = lib().odo_tracker_enqueue_dev_u8 if u8 else lib().odo_tracker_enqueue_dev
+        if fn(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr)) != 0:
             raise OdoError(self.ctx.last_error())
 
     def collect(self):
@@ -476,8 +489,9 @@ class Tracker:
         rs = [np.ascontiguousarray(a, dtype=dt) for a in rights]
         return self.step_ptrs([a.ctypes.data for a in ls], [a.ctypes.data for a in rs], u8=u8)
 
-    def step_dev(self, left_dev_ptr, right_dev_ptr):
-        rc = lib().odo_tracker_step_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr), *self._outs())
+    def step_dev(self, left_dev_ptr, right_dev_ptr, u8=False):
+        fn = lib().odo_tracker_step_dev_u8 if u8 else lib().odo_tracker_step_dev
+        rc = fn(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr), *self._outs())
         return self._result(rc)
 
     def stage_ms(self):

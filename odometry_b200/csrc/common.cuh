@@ -85,14 +85,25 @@ struct QuantOut {
   int pitch = 0;
   int* exact = nullptr;
 };
-void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
+// A batch of source frames: CV_32F (the hot path's PixelType) or CV_8U as imread(GRAYSCALE) leaves them; the kernels
+// that read raw frames convert u8 on load (exactly convertTo(CV_32F)), so a u8 frame never needs a float copy.
+struct ImgSrc {
+  const void* p = nullptr;
+  int u8 = 0;
+  ImgSrc() {}
+  ImgSrc(const float* f) : p(f), u8(0) {}
+  ImgSrc(const uint8_t* b) : p(b), u8(1) {}
+  const float* f32() const { return u8 ? nullptr : static_cast<const float*>(p); }
+  const uint8_t* b8() const { return u8 ? static_cast<const uint8_t*>(p) : nullptr; }
+};
+void launch_blur3(odo_ctx* c, ImgSrc src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
                   QuantOut q = QuantOut());
-void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
+void launch_pyrdown(odo_ctx* c, ImgSrc src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
                     int dw, int dh, int batch);
 // part: the tracker builds level 0 (needed by the depth stage) on its main stream and levels 1.. (needed only by the LM
 // solve) on the LM stream
 enum { PYR_ALL = 0, PYR_LEVEL0 = 1, PYR_UPPER_LEVELS = 2 };
-void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
+void launch_image_pyramid(odo_ctx* c, ImgSrc img, int64_t istride, float* pyr, int64_t pstride,
                           const PyrGeom& g, int smooth, int batch, QuantOut q0 = QuantOut(), int part = PYR_ALL);
 void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,
                           const PyrGeom& g, int smooth, int batch);
@@ -209,10 +220,11 @@ void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debu
 // blur_left_done: d.blurL already holds GaussianBlur(L) (image pyramid level 0 of the same frame)
 QuantOut depth_quant_left(const DepthWork& d, const odo_depth_params& p, int w, int h);  // q output of the left blur
 void depth_quant_reset(odo_ctx* c, const DepthWork& d, int batch);  // exact[b] = 1 before the frame's blurs
-void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+void launch_select(odo_ctx* c, ImgSrc L, ImgSrc R, int64_t stride, int w, int h,
                    const odo_depth_params& p, DepthWork& d, int batch, bool blur_left_done = false);
 void launch_disparity(odo_ctx* c, int w, int h, const odo_depth_params& p, DepthWork d, int batch);
-void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+// L / R: the RAW frames.  u8 frames are read as they are (left intensity per slot, right texels through rawR8).
+void launch_depth_refine(odo_ctx* c, ImgSrc L, ImgSrc R, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch);
 
 // ---- camera.cu -----------------------------------------------------------------------------------

@@ -966,6 +966,7 @@ __device__ __forceinline__ RefTexels ref_texels(const float* __restrict__ Rf, co
 // uniform over the pass (the pending decision, 1 + lambda) is folded into selects on uniform values.
 struct RefPass {
   const float* __restrict__ L;
+  const uint8_t* __restrict__ L8;   // u8 frames: the raw left image as it came in (L == nullptr then)
   const float* __restrict__ R;
   const uint8_t* __restrict__ R8;
   float* dep;
@@ -1013,7 +1014,7 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
       for (int u = 0; u < kRefUnroll; u++) {
         if (sb[u].x < 0) continue;
         const int o = (sb[u].x >> 16) * rp.W + (sb[u].x & 0xffff);
-        sb[u].y = __float_as_int(__ldg(rp.L + o));
+        sb[u].y = __float_as_int(rp.L8 ? (float)__ldg(rp.L8 + o) : __ldg(rp.L + o));
         const float d0 = rp.dep[o];  // init_depth / current_depth / tmp_depth, :105-139
         sa[u].x = d0;
         sa[u].y = d0;
@@ -1069,7 +1070,8 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
   }
 }
 
-__global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restrict__ Limg, const float* __restrict__ Rimg,
+__global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restrict__ Limg, const uint8_t* __restrict__ Limg8,
+                                                          const float* __restrict__ Rimg,
                                                           int64_t stride, int W, int H, odo_depth_params p,
                                                           DepthWork d, double* partials, unsigned* barrier,
                                                           int* abort_flags, int jb_in_smem,
@@ -1093,8 +1095,9 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   float* dep = d.dep + b * d.dep_stride;
   uint8_t* val = d.val + b * npx;
   RefPass rp;
-  rp.L = Limg + b * stride;
-  rp.R = Rimg + b * stride;
+  rp.L = Limg ? Limg + b * stride : nullptr;
+  rp.L8 = Limg8 ? Limg8 + b * stride : nullptr;
+  rp.R = Rimg ? Rimg + b * stride : nullptr;
   rp.use8 = d.rawR8 != nullptr && d.raw_exact[b] != 0;
   rp.R8 = d.rawR8 ? d.rawR8 + b * d.rawR8_stride : nullptr;
   rp.dep = dep;
@@ -1312,7 +1315,7 @@ __global__ void __launch_bounds__(256) k_fill_planes(FillArgs a) {
   }
 }
 
-void launch_select(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+void launch_select(odo_ctx* c, ImgSrc L, ImgSrc R, int64_t stride, int w, int h,
                    const odo_depth_params& p, DepthWork& d, int batch, bool blur_left_done) {
   const size_t npx = (size_t)w * h;
   // cv::GaussianBlur on both images, :255-257 (with q = 16 * blur as a second output when the integer line
@@ -1412,8 +1415,16 @@ static size_t refine_smem_bytes(int cap, int G) {
   return sizeof(float2) * (size_t)trips * kRefThreads;
 }
 
-void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t stride, int w, int h,
+void launch_depth_refine(odo_ctx* c, ImgSrc Lsrc, ImgSrc Rsrc, int64_t stride, int w, int h,
                          const odo_depth_params& p, DepthWork d, int batch) {
+  const float* L = Lsrc.f32();
+  const uint8_t* L8 = Lsrc.b8();
+  const float* R = Rsrc.f32();
+  if (Rsrc.u8 && d.rawR8 == nullptr) {   // u8 right frames are the refinement's u8 plane as they are, and exact
+    d.rawR8 = Rsrc.b8();
+    d.rawR8_stride = stride;
+    cudaMemsetAsync(d.raw_exact, 0xff, sizeof(int) * batch, c->stream);
+  }
   static bool attr_done[64] = {false};  // per device: function attributes are per device
   if (!attr_done[c->device & 63]) {
     cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1487,12 +1498,12 @@ void launch_depth_refine(odo_ctx* c, const float* L, const float* R, int64_t str
     int W = w, H = h;
     int64_t st = stride;
     odo_depth_params pp = p;
-    void* args[] = {(void*)&L, (void*)&R, (void*)&st, (void*)&W, (void*)&H, (void*)&pp, (void*)&d,
+    void* args[] = {(void*)&L, (void*)&L8, (void*)&R, (void*)&st, (void*)&W, (void*)&H, (void*)&pp, (void*)&d,
                     (void*)&partials, (void*)&barrier, (void*)&abort_flag, (void*)&jb_in_smem,
                     (void*)&timeout_ns, (void*)&lose_cta};
     e = cudaLaunchCooperativeKernel((const void*)k_refine, grid, block, args, smem, c->stream);
   } else {
-    k_refine<<<grid, block, smem, c->stream>>>(L, R, stride, w, h, p, d, partials, barrier, abort_flag, jb_in_smem, timeout_ns,
+    k_refine<<<grid, block, smem, c->stream>>>(L, L8, R, stride, w, h, p, d, partials, barrier, abort_flag, jb_in_smem, timeout_ns,
                                                lose_cta);
     e = cudaGetLastError();
   }

@@ -48,9 +48,16 @@ __device__ __forceinline__ float tap121(float a, float b, float c) {
 // search (depth.cu): a value that is not a multiple of 1/16 in [0, 255] clears the sequence's `exact` flag.
 constexpr int kBlurRows = 16;
 
-__device__ __forceinline__ float blur_row(const float* __restrict__ p, int dm, int dp) {
+// A source pixel as the float the reference works on: CV_32F frames as they are, CV_8U frames through the exact
+// convertTo(CV_32F) of run_odometry_kitti_offline.cpp:348,358 -- the u8-native front end reads a quarter of the bytes
+// and needs no converted copy of the frame.
+__device__ __forceinline__ float px(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float px(const uint8_t* p) { return (float)__ldg(p); }
+
+template <typename SRC>
+__device__ __forceinline__ float blur_row(const SRC* __restrict__ p, int dm, int dp) {
   // horizontal pass at the column p points to; dm / dp are the (reflected) neighbour offsets, -1 / +1 inside
-  return tap121(__ldg(p + dm), __ldg(p), __ldg(p + dp));
+  return tap121(px(p + dm), px(p), px(p + dp));
 }
 
 __device__ __forceinline__ bool quant_store(uint16_t* q, float v) {
@@ -62,20 +69,20 @@ __device__ __forceinline__ bool quant_store(uint16_t* q, float v) {
   return ok;
 }
 
-template <bool QOUT>
-__global__ void __launch_bounds__(128, 8) k_blur3(const float* __restrict__ src, int64_t sstride,
+template <bool QOUT, typename SRC>
+__global__ void __launch_bounds__(128, 8) k_blur3(const SRC* __restrict__ src, int64_t sstride,
                                                float* __restrict__ dst, int64_t dstride, int w, int h, QuantOut q) {
   const int x = blockIdx.x * 128 + threadIdx.x;
   const int y0 = blockIdx.y * kBlurRows;
   bool bad = false;
   if (x < w) {
-    const float* s = src + (int64_t)blockIdx.z * sstride + x;
+    const SRC* s = src + (int64_t)blockIdx.z * sstride + x;
     float* d = dst + (int64_t)blockIdx.z * dstride + (int64_t)y0 * w + x;
     uint16_t* qd = QOUT ? q.plane + (int64_t)blockIdx.z * q.stride + (int64_t)y0 * q.pitch + x : nullptr;
     const int dm = reflect101(x - 1, w) - x, dp = reflect101(x + 1, w) - x;
     const int y1 = min(y0 + kBlurRows, h);
     float t0 = blur_row(s + (int64_t)reflect101(y0 - 1, h) * w, dm, dp);
-    const float* r = s + (int64_t)y0 * w;
+    const SRC* r = s + (int64_t)y0 * w;
     float t1 = blur_row(r, dm, dp);
     // rows whose successor is inside the image: the source pointer just advances
     const int ym = min(y1, h - 1);
@@ -106,9 +113,10 @@ __global__ void __launch_bounds__(128, 8) k_blur3(const float* __restrict__ src,
 }
 
 // horizontal 1-4-6-4-1 of one source row at even column 2x (unscaled)
-__device__ __forceinline__ float hrow5(const float* __restrict__ r, int i0, int i1, int i2, int i3, int i4,
+template <typename SRC>
+__device__ __forceinline__ float hrow5(const SRC* __restrict__ r, int i0, int i1, int i2, int i3, int i4,
                                        bool body) {
-  const float s0 = __ldg(r + i0), s1 = __ldg(r + i1), s2 = __ldg(r + i2), s3 = __ldg(r + i3), s4 = __ldg(r + i4);
+  const float s0 = px(r + i0), s1 = px(r + i1), s2 = px(r + i2), s3 = px(r + i3), s4 = px(r + i4);
   if (body)  // v_muladd(r2, 6, v_muladd(r1 + r3, 4, r0 + r4))
     return __fadd_rn(__fmul_rn(s2, 6.f), __fadd_rn(__fmul_rn(__fadd_rn(s1, s3), 4.f), __fadd_rn(s0, s4)));
   // src[2x]*6 + (src[2x-1] + src[2x+1])*4 + src[2x-2] + src[2x+2], left to right
@@ -119,13 +127,14 @@ __device__ __forceinline__ float hrow5(const float* __restrict__ r, int i0, int 
 // Same strip structure as k_blur3: a thread walks down one output column; consecutive output rows share three
 // of their five horizontally filtered source rows, so each step filters two new source rows.
 constexpr int kDownRows = 8;
-__global__ void __launch_bounds__(128) k_pyrdown(const float* __restrict__ src, int64_t sstride, int sw, int sh,
+template <typename SRC>
+__global__ void __launch_bounds__(128) k_pyrdown(const SRC* __restrict__ src, int64_t sstride, int sw, int sh,
                                                  float* __restrict__ dst, int64_t dstride, int dw, int dh,
                                                  int hbody_end, int vbody_end) {
   const int x = blockIdx.x * 128 + threadIdx.x;
   const int y0 = blockIdx.y * kDownRows;
   if (x >= dw) return;
-  const float* s = src + (int64_t)blockIdx.z * sstride;
+  const SRC* s = src + (int64_t)blockIdx.z * sstride;
   float* d = dst + (int64_t)blockIdx.z * dstride + (int64_t)y0 * dw + x;
   const int i0 = reflect101(2 * x - 2, sw), i1 = reflect101(2 * x - 1, sw), i2 = reflect101(2 * x, sw),
             i3 = reflect101(2 * x + 1, sw), i4 = reflect101(2 * x + 2, sw);
@@ -244,15 +253,22 @@ void launch_u8_to_f32(odo_ctx* c, const uint8_t* src, float* dst, int64_t n) {
   c->launches++;
 }
 
-void launch_blur3(odo_ctx* c, const float* src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
+void launch_blur3(odo_ctx* c, ImgSrc src, int64_t sstride, float* dst, int64_t dstride, int w, int h, int batch,
                   QuantOut q) {
   dim3 grid((w + 127) / 128, (h + kBlurRows - 1) / kBlurRows, batch);
-  if (q.plane) k_blur3<true><<<grid, 128, 0, c->stream>>>(src, sstride, dst, dstride, w, h, q);
-  else k_blur3<false><<<grid, 128, 0, c->stream>>>(src, sstride, dst, dstride, w, h, q);
+  if (src.u8) {
+    const uint8_t* s8 = static_cast<const uint8_t*>(src.p);
+    if (q.plane) k_blur3<true, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+    else k_blur3<false, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+  } else {
+    const float* sf = static_cast<const float*>(src.p);
+    if (q.plane) k_blur3<true, float><<<grid, 128, 0, c->stream>>>(sf, sstride, dst, dstride, w, h, q);
+    else k_blur3<false, float><<<grid, 128, 0, c->stream>>>(sf, sstride, dst, dstride, w, h, q);
+  }
   c->launches++;
 }
 
-void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
+void launch_pyrdown(odo_ctx* c, ImgSrc src, int64_t sstride, int sw, int sh, float* dst, int64_t dstride,
                     int dw, int dh, int batch) {
   // column split of OpenCV's pyrDown_ for a 4-lane (SSE-baseline) build, see oracle/imgproc.cpp
   const int lanes = 4;
@@ -261,25 +277,33 @@ void launch_pyrdown(odo_ctx* c, const float* src, int64_t sstride, int sw, int s
   const int hbody_end = (width0 > 1) ? 1 + lanes * ((width0 - 1) / lanes) : 1;
   const int vbody_end = lanes * (dw / lanes);
   dim3 grid((dw + 127) / 128, (dh + kDownRows - 1) / kDownRows, batch);
-  k_pyrdown<<<grid, 128, 0, c->stream>>>(src, sstride, sw, sh, dst, dstride, dw, dh, hbody_end, vbody_end);
+  if (src.u8)
+    k_pyrdown<uint8_t><<<grid, 128, 0, c->stream>>>(static_cast<const uint8_t*>(src.p), sstride, sw, sh, dst, dstride, dw, dh,
+                                                     hbody_end, vbody_end);
+  else
+    k_pyrdown<float><<<grid, 128, 0, c->stream>>>(static_cast<const float*>(src.p), sstride, sw, sh, dst, dstride, dw, dh,
+                                                   hbody_end, vbody_end);
   c->launches++;
 }
 
-void launch_image_pyramid(odo_ctx* c, const float* img, int64_t istride, float* pyr, int64_t pstride,
+void launch_image_pyramid(odo_ctx* c, ImgSrc img, int64_t istride, float* pyr, int64_t pstride,
                           const PyrGeom& g, int smooth, int batch, QuantOut q0, int part) {
   const int64_t n0 = (int64_t)g.w[0] * g.h[0];
   if (part != PYR_UPPER_LEVELS) {
     if (smooth) {
       launch_blur3(c, img, istride, pyr, pstride, g.w[0], g.h[0], batch, q0);
+    } else if (img.u8) {   // level 0 = convertTo(CV_32F) of the frame
+      for (int b = 0; b < batch; b++)
+        launch_u8_to_f32(c, static_cast<const uint8_t*>(img.p) + (int64_t)b * istride, pyr + (int64_t)b * pstride, n0);
     } else {
-      launch_copy_batched(c, img, istride, pyr, pstride, n0, batch);
+      launch_copy_batched(c, static_cast<const float*>(img.p), istride, pyr, pstride, n0, batch);
     }
   }
   if (part == PYR_LEVEL0) return;
   if (g.levels > 1)  // level 1 from the RAW input (quirk Q5)
     launch_pyrdown(c, img, istride, g.w[0], g.h[0], pyr + g.off[1], pstride, g.w[1], g.h[1], batch);
   for (int l = 2; l < g.levels; l++)
-    launch_pyrdown(c, pyr + g.off[l - 1], pstride, g.w[l - 1], g.h[l - 1], pyr + g.off[l], pstride, g.w[l], g.h[l], batch);
+    launch_pyrdown(c, ImgSrc(pyr + g.off[l - 1]), pstride, g.w[l - 1], g.h[l - 1], pyr + g.off[l], pstride, g.w[l], g.h[l], batch);
 }
 
 void launch_depth_pyramid(odo_ctx* c, const float* dep, int64_t dstride, float* pyr, int64_t pstride,

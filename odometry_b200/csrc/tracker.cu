@@ -248,8 +248,11 @@ struct StreamScope {
 };
 
 // queues all kernels of one frame (one frame per sequence) on the compute stream; no host wait
-// R8: the raw right frames as u8 when the caller already has them on the device (u8 ingest), else nullptr
-static int tracker_launch(odo_tracker* t, const float* L, const float* R, int slot, const uint8_t* R8 = nullptr) {
+// L, R: the raw frames of the batch, CV_32F or CV_8U (u8-native front end: every kernel that reads a raw frame converts
+// on load, nothing is converted ahead).  R8: the raw right frames as u8 when a float R comes with a u8 twin (raw-camera
+// ingest), else nullptr.
+static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const uint8_t* R8 = nullptr) {
+  if (R.u8) R8 = R.b8();
   odo_ctx* c = t->c;
   const int n = t->n;
   const int first = (t->frame_id == 0) ? 1 : 0;
@@ -383,13 +386,11 @@ static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const*
   }
   ODO_CUDA_OK(c, cudaEventRecord(t->ev_copied[slot], t->copy_stream));
   ODO_CUDA_OK(c, cudaStreamWaitEvent(c->stream, t->ev_copied[slot], 0));
-  if (u8) {
-    // gray_8u.convertTo(gray, CV_32F), run_odometry_kitti_offline.cpp:348,358
-    launch_u8_to_f32(c, t->in_u8[slot], t->in_left[slot], t->npx * t->n);
-    launch_u8_to_f32(c, t->in_u8[slot] + (size_t)t->n * t->npx, t->in_right[slot], t->npx * t->n);
-  }
-  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, u8 ? t->in_u8[slot] + (size_t)t->n * t->npx : nullptr) != 0)
-    return tracker_break(t);
+  // u8 frames (what imread(GRAYSCALE) returns) stay u8 on the device: gray_8u.convertTo(gray, CV_32F),
+  // run_odometry_kitti_offline.cpp:348,358, happens on load inside the blur / pyrDown / refinement kernels
+  const ImgSrc Ls = u8 ? ImgSrc(t->in_u8[slot]) : ImgSrc(t->in_left[slot]);
+  const ImgSrc Rs = u8 ? ImgSrc(t->in_u8[slot] + (size_t)t->n * t->npx) : ImgSrc(t->in_right[slot]);
+  if (tracker_launch(t, Ls, Rs, slot) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
@@ -652,7 +653,7 @@ int odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, c
     c->err = "tracker: remap launch failed";
     return -1;
   }
-  if (tracker_launch(t, t->in_left[slot], t->in_right[slot], slot, R8) != 0) return tracker_break(t);
+  if (tracker_launch(t, ImgSrc(t->in_left[slot]), ImgSrc(t->in_right[slot]), slot, R8) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
@@ -673,9 +674,30 @@ int odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* 
     return -1;
   }
   const int slot = (int)(t->n_enqueued & 1);
-  if (tracker_launch(t, left_dev, right_dev, slot) != 0) return tracker_break(t);
+  if (tracker_launch(t, ImgSrc(left_dev), ImgSrc(right_dev), slot) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
+}
+
+int odo_tracker_enqueue_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint8_t* right_dev) {
+  if (!tracker_usable(t) || !left_dev || !right_dev) return -1;
+  odo_ctx* c = t->c;
+  ODO_CUDA_OK(c, cudaSetDevice(c->device));
+  if (t->n_enqueued - t->n_collected >= 2) {
+    c->err = "tracker: two frames are already in flight, collect one first";
+    return -1;
+  }
+  const int slot = (int)(t->n_enqueued & 1);
+  if (tracker_launch(t, ImgSrc(left_dev), ImgSrc(right_dev), slot) != 0) return tracker_break(t);
+  t->n_enqueued++;
+  return 0;
+}
+
+int odo_tracker_step_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint8_t* right_dev, float* pose_abs,
+                            float* pose_kf, int* is_keyframe, int* status) {
+  if (!t || t->n_enqueued != t->n_collected) return -1;
+  if (odo_tracker_enqueue_dev_u8(t, left_dev, right_dev) != 0) return -1;
+  return odo_tracker_collect(t, pose_abs, pose_kf, is_keyframe, status);
 }
 
 int odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev, float* pose_abs,

@@ -62,6 +62,24 @@ def test_u8_ingest_equals_float_ingest(ctx, synth_data):
     b.close()
 
 
+def test_device_resident_u8_frames_equal_float_ingest(ctx, synth_data):
+    """odo_tracker_step_dev_u8 (CV_8U frames resident in HBM, converted on load inside the blur / pyrDown / refinement
+    kernels) returns the bits of the CV_32F host entry point, across a keyframe switch."""
+    import torch
+    seqs = [synth_data.sequence(s, n_frames=7) for s in (0, 1)]
+    a = capi.Tracker(ctx, 1241, 376, 4, 2)
+    b = capi.Tracker(ctx, 1241, 376, 4, 2)
+    for k in range(7):
+        ra = a.step([s["frames"][k][0].astype(np.float32) for s in seqs], [s["frames"][k][1].astype(np.float32) for s in seqs])
+        L = torch.from_numpy(np.stack([s["frames"][k][0] for s in seqs])).cuda()
+        R = torch.from_numpy(np.stack([s["frames"][k][1] for s in seqs])).cuda()
+        rb = b.step_dev(L.data_ptr(), R.data_ptr(), u8=True)
+        assert ra[0] == rb[0] == 0
+        assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
+    a.close()
+    b.close()
+
+
 def test_batched_sequences_equal_single_runs(ctx, synth_data):
     """Per-sequence results are bit-identical whether a sequence runs alone or inside a batch
     (the property that makes the multi-GPU sharding of config 4 exact)."""
