@@ -1088,8 +1088,11 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   gs.target = 0;
   gs.parity = 0;
   gs.G = G;
-  int* abort_flag = gs.abort_flag;
+  __shared__ int s_aborted;
+  gs.s_abort = &s_aborted;
   if (lose_cta && G > 1 && blockIdx.x == G - 1) return;   // test hook: a CTA that never arrives
+  if (threadIdx.x == 0) s_aborted = 0;
+  __syncthreads();
   const int64_t npx = (int64_t)W * H;
   odo_depth_stats* stats = d.stats + b;
   float* dep = d.dep + b * d.dep_stride;
@@ -1142,7 +1145,7 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
     err_now = (float)(sh.tot[0] / sh.tot[1]);
     __syncthreads();
     cyc_red += clock64() - t1;
-    if (*(volatile int*)abort_flag) { pending = PEND_NONE; break; }
+    if (s_aborted) { pending = PEND_NONE; break; }   // set by the barrier this CTA just left
     if (err_now > err_last) {  // :147-151
       lambda = lambda * 10.0f;
       if (lambda > 1e+5f) { pending = PEND_NONE; break; }  // break BEFORE current = pre
@@ -1199,7 +1202,7 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
     stats->cost = err_now;
     int status = (n_valid < 500) ? -1 : 0;  // :192-197
     if (too_many) status = -1;
-    if (*(volatile int*)abort_flag) status = ODO_STATUS_BARRIER_TIMEOUT;   // not a failure of the algorithm: reported apart
+    if (s_aborted) status = ODO_STATUS_BARRIER_TIMEOUT;   // not a failure of the algorithm: reported apart
     stats->status = status;
     if (b == 0 && d.dbg) {
       d.dbg[0] = cyc_first; d.dbg[1] = cyc_pass; d.dbg[2] = cyc_red; d.dbg[3] = t_loop_end - t_begin;

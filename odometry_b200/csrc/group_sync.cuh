@@ -22,6 +22,8 @@ struct GroupSync {
   unsigned target;      // barrier generation target (meaningful in thread 0)
   int parity;
   int G;
+  int* s_abort;         // SHARED memory word of the CTA: set once a barrier of this group gave up, so the kernels
+                        // learn about it from the barrier they just left instead of polling the global flag
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -50,11 +52,12 @@ __device__ __forceinline__ void group_barrier(GroupSync& gs) {
     unsigned long long t0 = 0;
     while (ld_acquire_u32(gs.counter) < gs.target) {
       if ((++spins & 255u) == 0u) {
-        if (*(volatile int*)gs.abort_flag) break;
+        if (*(volatile int*)gs.abort_flag) { *gs.s_abort = 1; break; }
         const unsigned long long now = global_timer_ns();
         if (t0 == 0) t0 = now;
         else if (now - t0 > gs.timeout_ns) {
           atomicExch(gs.abort_flag, 1);
+          *gs.s_abort = 1;
           break;
         }
       }

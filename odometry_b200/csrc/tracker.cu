@@ -378,11 +378,32 @@ static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const*
   // the slot's previous frame (two enqueues ago) must have been consumed by its kernels
   if (t->n_enqueued >= 2) ODO_CUDA_OK(c, cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[slot], 0));
   const size_t bytes = sizeof(T) * (size_t)t->npx;
-  for (int b = 0; b < t->n; b++) {
-    void* dl = u8 ? (void*)(t->in_u8[slot] + (size_t)b * t->npx) : (void*)(t->in_left[slot] + (size_t)b * t->npx);
-    void* dr = u8 ? (void*)(t->in_u8[slot] + (size_t)(t->n + b) * t->npx) : (void*)(t->in_right[slot] + (size_t)b * t->npx);
-    ODO_CUDA_OK(c, cudaMemcpyAsync(dl, left[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
-    ODO_CUDA_OK(c, cudaMemcpyAsync(dr, right[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
+  void* dl0 = u8 ? (void*)t->in_u8[slot] : (void*)t->in_left[slot];
+  void* dr0 = u8 ? (void*)(t->in_u8[slot] + (size_t)t->n * t->npx) : (void*)t->in_right[slot];
+  // Host images that sit at a constant distance from each other (one allocation holding the batch, the usual case) go
+  // over in ONE strided copy per eye: 2 * n_seq separate 0.5 MB copies cost more in DMA set-up than in transfer and
+  // made the copy stream, not the kernels, the pace of the pipelined ingest (measured: 25 GB/s of a 55 GB/s link).
+  auto strided = [&](const T* const* img, ptrdiff_t* stride) {
+    if (t->n < 2) return false;
+    const ptrdiff_t d = (const char*)img[1] - (const char*)img[0];
+    if (d < (ptrdiff_t)bytes || d > (ptrdiff_t)1 << 30) return false;   // cudaMemcpy2D pitches are limited (memPitch)
+    for (int b = 2; b < t->n; b++)
+      if ((const char*)img[b] - (const char*)img[b - 1] != d) return false;
+    *stride = d;
+    return true;
+  };
+  ptrdiff_t sl = 0, sr = 0;
+  bool copied = false;
+  if (strided(left, &sl) && strided(right, &sr)) {
+    copied = cudaMemcpy2DAsync(dl0, bytes, left[0], (size_t)sl, bytes, (size_t)t->n, cudaMemcpyHostToDevice, t->copy_stream) == cudaSuccess &&
+             cudaMemcpy2DAsync(dr0, bytes, right[0], (size_t)sr, bytes, (size_t)t->n, cudaMemcpyHostToDevice, t->copy_stream) == cudaSuccess;
+    if (!copied) cudaGetLastError();   // not a layout the 2-D copy takes: fall back to one copy per image
+  }
+  if (!copied) {
+    for (int b = 0; b < t->n; b++) {
+      ODO_CUDA_OK(c, cudaMemcpyAsync((char*)dl0 + (size_t)b * bytes, left[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
+      ODO_CUDA_OK(c, cudaMemcpyAsync((char*)dr0 + (size_t)b * bytes, right[b], bytes, cudaMemcpyHostToDevice, t->copy_stream));
+    }
   }
   ODO_CUDA_OK(c, cudaEventRecord(t->ev_copied[slot], t->copy_stream));
   ODO_CUDA_OK(c, cudaStreamWaitEvent(c->stream, t->ev_copied[slot], 0));
