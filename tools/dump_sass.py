@@ -10,8 +10,12 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OBJ = {"k_disparity": "depth.o", "k_refine": "depth.o", "k_select_warp": "depth.o", "k_lm_solve": "lm.o", "k_lm_fill": "lm.o",
-       "k_blur3": "pyramid.o", "k_pyrdown": "pyramid.o", "k_front": "pyramid.o", "k_remap": "camera.o"}
+OBJ = {"k_disparity": "depth.o", "k_refine": "depth.o", "k_select_tile": "depth.o", "k_lm_solve": "lm.o", "k_lm_fill": "lm.o",
+       "k_blur3": "pyramid.o", "k_pyrdown": "pyramid.o", "k_remap": "camera.o"}
+# the template instances the KITTI step launches (the listings of the other instances differ only in constants)
+KEEP = {"k_disparity": r"k_disparity<\(bool\)1, \(int\)1280, \(bool\)1>", "k_lm_solve": r"k_lm_solve<\(bool\)0>",
+        "k_blur3": r"k_blur3<\(bool\)1, unsigned char>", "k_pyrdown": r"k_pyrdown<(unsigned char|float)>",
+        "k_remap": r"k_remap<unsigned char>"}
 WATCH = ["IMAD", "IDP", "FFMA", "FMUL", "FADD", "DFMA", "DADD", "DMUL", "LDG", "STG", "LDS", "STS", "SHFL", "REDUX", "VOTE",
          "BAR", "MUFU", "ATOM", "RED", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "LDTM", "UTCMMA", "UTCHMMA", "SYNCS"]
 
@@ -27,6 +31,10 @@ def main():
             cache[path] = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
         funcs = re.split(r"(?=\n\s*Function : )", cache[path])
         mine = [f for f in funcs if re.search(r"Function : \S*" + kern, f)]
+        if kern in KEEP:
+            def dem(f):
+                return subprocess.run(["cu++filt", re.search(r"Function : (\S+)", f).group(1)], capture_output=True, text=True).stdout
+            mine = [f for f in mine if re.search(KEEP[kern], dem(f))]
         if not mine:
             continue
         with open(os.path.join(out_dir, f"sass_{kern}.txt"), "w") as fh:
