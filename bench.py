@@ -970,9 +970,10 @@ def run_kitti(args, rank, local_rank, world):
     critical = [k for k in stage_ms if k != "lm_solve"]
     dom = max(critical, key=lambda k: stage_ms[k])
     traffic = None
+    prof = {}
     try:
         import glob
-        prof = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_traffic.json")))[-1]))  # newest capture
+        prof = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_r*_traffic.json")), key=os.path.getmtime)[-1]))  # newest capture
         if prof.get("sequences_per_launch") == St and dom in prof.get("stage_dram_bytes", {}):
             traffic = prof["stage_dram_bytes"][dom]
     except Exception:
@@ -988,6 +989,27 @@ def run_kitti(args, rank, local_rank, world):
             "per_stage_gbs": {k: alg_bytes[k] * St / (stage_ms[k] * 1e-3) / 1e9 for k in alg_bytes if stage_ms.get(k)},
             "hbm_note": "frac = algorithmic HBM bytes of the dominant kernel / its time / HBM peak (the contract's definition); "
                         "the line search is bound by instruction issue, not HBM: see issue_roofline"}
+    # the kernels of the critical path are bound by instruction issue, not by HBM: achieved warp instructions per second
+    # (instruction count of the committed ncu capture of the same launch shape / the live launch time) against the
+    # issue slots of the device (SMs x 4 schedulers x clock)
+    try:
+        kname = {"disparity": "k_disparity<1, 1280, 1>", "depth_refine": "k_refine", "blur_select": "k_select_tile<28>"}.get(dom)
+        kinfo = prof.get("kernels", {}).get(kname) if prof.get("sequences_per_launch") == St else None
+        if kinfo and kinfo.get("warp_inst_per_launch"):
+            sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = sm * 4 * clk
+            # the stage may hold small helper kernels besides the dominant one: scale the stage time by the kernel's share
+            share = kinfo["ms_per_launch"] / max(prof["stage_ms_serialised"].get(dom, kinfo["ms_per_launch"]), 1e-9)
+            t_k = stage_ms[dom] * min(share, 1.0) * 1e-3
+            roof["issue"] = {"bound": "issue", "kernel": kname, "unit": "warp instructions/s",
+                             "warp_instructions_per_launch": kinfo["warp_inst_per_launch"],
+                             "achieved": kinfo["warp_inst_per_launch"] / t_k, "peak": peak_issue,
+                             "frac": kinfo["warp_inst_per_launch"] / t_k / peak_issue,
+                             "ncu_issue_active_pct": kinfo.get("issue_active_pct"),
+                             "source": prof.get("source")}
+    except Exception as e:
+        roof["issue"] = {"error": str(e)}
     if dom == "disparity":
         # the line search is bound by integer-multiply issue, not by HBM: 8 IMAD per (pixel, candidate) on the
         # half-rate fmaheavy pipe (ncu: sm__pipe_fmaheavy_cycles_active).  Candidate evaluations of one frame are

@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(i):
         if not force and _newer(objs[i], [srcs[i]] + hdrs):
             return
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcs[i], "-o", objs[i]]
+        extra = os.environ.get("ODO_EXTRA_NVCC", "").split()   # experiment knob (e.g. -DODO_LM_THREADS=256)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcs[i], "-o", objs[i]]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -502,7 +502,16 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   t->h_state[1] = t->h_state[0] + n_seq;
   cudaError_t ce = cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking);
   auto ok = [&ce](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
-  ok(cudaStreamCreateWithFlags(&t->lm_stream, cudaStreamNonBlocking));
+  {
+    // The LM solve is the latency chain of the frame; its one-CTA-per-SM blocks need a whole SM's registers and would
+    // otherwise queue behind the thousands of small blocks of the depth kernels: highest stream priority lets the
+    // block scheduler hand drained SMs to the solve first (ODO_LM_STREAM_PRIORITY=0: plain stream, A/B switch).
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const char* e = std::getenv("ODO_LM_STREAM_PRIORITY");
+    const bool prio = !(e && e[0] == '0');
+    ok(cudaStreamCreateWithPriority(&t->lm_stream, cudaStreamNonBlocking, prio ? hi : 0));
+  }
   ok(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming));
   for (int k = 0; k < 2; k++)

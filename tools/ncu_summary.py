@@ -43,7 +43,7 @@ COLS = [
 STAGES = {
     "image_pyramid": ["k_blur3", "k_pyrdown:3"],
     "lm_solve": ["k_lm_solve", "k_track_pose"],
-    "blur_select": ["k_blur3", "k_select"],
+    "blur_select": ["k_blur3", "k_fill_planes", "k_select"],
     "disparity": ["k_disparity<1", "k_disparity<0"],
     "depth_refine": ["k_raw8", "k_refine"],
     "depth_pyr_promote_prepare": ["k_track_finalize", "k_lm_count", "k_lm_scan", "k_lm_fill"],
@@ -106,11 +106,14 @@ def main():
             else:
                 cells.append(f"{v:.1f}")
         lines.append(f"| {name} | " + " | ".join(cells) + " |")
-        k = per_kernel.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0})
+        k = per_kernel.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0, "warp_inst": 0.0, "issue_pct": 0.0})
         k["launches"] += 1
+        k["warp_inst"] += val(r, "smsp__inst_executed.sum") or 0.0
+        k["issue_pct"] += val(r, "sm__inst_issued.avg.pct_of_peak_sustained_active") or 0.0
         k["dram_bytes"] += (val(r, "dram__bytes_read.sum") or 0.0) + (val(r, "dram__bytes_write.sum") or 0.0)
         k["ms"] += val(r, "gpu__time_duration.sum") or 0.0
     kernels = {n: {"dram_bytes_per_launch": k["dram_bytes"] / k["launches"], "ms_per_launch": k["ms"] / k["launches"],
+                   "warp_inst_per_launch": k["warp_inst"] / k["launches"], "issue_active_pct": k["issue_pct"] / k["launches"],
                    "launches_in_capture": k["launches"]} for n, k in per_kernel.items()}
     stage_bytes, stage_ms = {}, {}
     for stage, pats in STAGES.items():
