@@ -51,7 +51,8 @@ def host_cpu():
 
 CPU_KIND_NOTE = {
     "reference": "the reference's own classes (oracle/_ref: its hot-path sources compiled unmodified against stand-in "
-                 "Eigen/OpenCV/Sophus headers, the loop of run_odometry_kitti_offline.cpp:95-271 around them); host: " + host_cpu(),
+                 "Eigen/OpenCV/Sophus headers, the loop of run_odometry_kitti_offline.cpp:95-271 around them; the stand-in's "
+                 "matrix products are scalar loops, so a build against real, vectorised Eigen may be faster); host: " + host_cpu(),
     "port": "oracle port of the reference (oracle/_ref not present); host: " + host_cpu(),
 }
 

@@ -22,9 +22,15 @@ SUM_PAIRWISE = 3    # (tools/association_noise.py)
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (g++ only)."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+    if force or not os.path.exists(_LIB_PATH) or os.path.exists(os.path.join(_HERE, "Makefile")) and _stale():
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return _LIB_PATH
+
+
+def _stale() -> bool:
+    """the library is older than one of its sources (make decides; this only avoids spawning it on every import)"""
+    t = os.path.getmtime(_LIB_PATH)
+    return any(f.endswith((".cpp", ".h")) and os.path.getmtime(os.path.join(_HERE, f)) > t for f in os.listdir(_HERE))
 
 
 class Intrinsics(C.Structure):
