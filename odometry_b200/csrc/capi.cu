@@ -234,6 +234,7 @@ static int lm_group_size(const odo_ctx* c, const PyrGeom& g) {
   int G = (int)((n0 + 16383) / 16384);
   const int cap = lm_max_ctas(c);
   if (G > cap) G = cap;
+  if (G > 16 && G <= 32) G = 16;   // KITTI-sized frames: one thread-block cluster per solve (lm.cu, launch_lm_solve)
   if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // test / experiment knob (the tracker reads it too)
     const int g = std::atoi(e);
     if (g >= 1 && g <= cap) G = g;

@@ -1090,6 +1090,7 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   gs.G = G;
   __shared__ int s_aborted;
   gs.s_abort = &s_aborted;
+  gs.s_part = nullptr;   // global-memory partials + counter barrier (cooperative launch)
   if (lose_cta && G > 1 && blockIdx.x == G - 1) return;   // test hook: a CTA that never arrives
   if (threadIdx.x == 0) s_aborted = 0;
   __syncthreads();

@@ -8,6 +8,7 @@
 // that all CTAs of a group are co-resident.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -24,6 +25,10 @@ struct GroupSync {
   int G;
   int* s_abort;         // SHARED memory word of the CTA: set once a barrier of this group gave up, so the kernels
                         // learn about it from the barrier they just left instead of polling the global flag
+  // Thread-block CLUSTER mode (G <= 16 CTAs launched as one cluster): the partials stay in each CTA's shared memory
+  // (s_part, [2][32] doubles), the barrier is the hardware cluster barrier and the other CTAs' partials are read
+  // through distributed shared memory -- no L2 round trips, no spinning, co-scheduling guaranteed by the hardware.
+  double* s_part;       // SHARED memory of this CTA, or nullptr: global-memory partials + counter barrier
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -111,21 +116,36 @@ __device__ __forceinline__ void group_allreduce(double* vals, double (*s_warp)[3
     for (int w = 0; w < WARPS; w++) s += s_warp[w][threadIdx.x];
     if (gs.G == 1) {
       s_tot[threadIdx.x] = s;
+    } else if (gs.s_part) {
+      gs.s_part[gs.parity * 32 + threadIdx.x] = s;
     } else {
       __stcg(gs.partials + ((int64_t)gs.parity * gs.G + blockIdx.x) * 32 + threadIdx.x, s);
     }
   }
   if (gs.G > 1) {
-    group_barrier(gs);
     // every CTA adds the G partials in the same fixed order, with the loads spread over the warps: warp w takes
     // partials w, w + WARPS, ... (lane = value index), then the WARPS sub-sums are added in warp order.  (One thread
     // per value walking all G partials costs G dependent L2 round trips: 9 us per LM iteration at G = 29.)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double s = 0.0;
-    if (lane < NV) {
-      const double* p = gs.partials + (int64_t)gs.parity * gs.G * 32 + lane;
+    if (gs.s_part) {
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();   // release / acquire over the whole cluster: every CTA's partial of this parity is visible
+      if (lane < NV) {
+        double* mine = gs.s_part + gs.parity * 32 + lane;
 #pragma unroll 4
-      for (int c = wid; c < gs.G; c += WARPS) s += __ldcg(p + (int64_t)c * 32);
+        for (int c = wid; c < gs.G; c += WARPS) s += *cluster.map_shared_rank(mine, c);
+      }
+      // no second cluster barrier: the next reduce writes the OTHER parity buffer, and nobody can reach the reduce after
+      // that (same buffer again) before all CTAs have passed the next cluster.sync(), i.e. finished these reads
+    } else {
+      group_barrier(gs);
+      if (lane < NV) {
+        const double* p = gs.partials + (int64_t)gs.parity * gs.G * 32 + lane;
+#pragma unroll 4
+        for (int c = wid; c < gs.G; c += WARPS) s += __ldcg(p + (int64_t)c * 32);
+      }
     }
     s_warp[wid][lane] = s;
     __syncthreads();

@@ -445,6 +445,7 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   int G = c->sm_count / (2 * n_seq);
   const int gmax = (int)((t->npx + 16383) / 16384);
   if (G > gmax) G = gmax;
+  if (G > 16 && G <= 32) G = 16;   // one thread-block cluster per sequence (DSMEM reduce) beats 29 CTAs on the global barrier
   if (G < 1) G = 1;
   if (const char* e = std::getenv("ODO_LM_CTAS_PER_SEQ")) {  // experiment knob
     const int g = std::atoi(e);
