@@ -49,14 +49,17 @@ def test_refine_group_sizes_agree(ctx, pair):
 def test_lm_group_sizes_agree(ctx, pair):
     rc, val, disp, dep, st = ctx.compute_depth(pair["L1"], pair["R1"], capi.default_depth_params())
     p1, d1, p2 = ctx.image_pyramid(pair["L1"], LEVELS, True), ctx.depth_pyramid(dep, LEVELS, False), ctx.image_pyramid(pair["L2"], LEVELS, True)
-    base = ctx.lm_solve(p1, d1, p2, capi.default_lm_params())      # G = 29 for one KITTI frame
+    base = ctx.lm_solve(p1, d1, p2, capi.default_lm_params())      # G = 16 for one KITTI frame: one cluster
     lin = ctx.lm_linearize(p1, d1, p2, 0, np.eye(4, dtype=np.float32))
     assert base[0] == 0
-    for g in (1, 3):
-        with env(ODO_LM_CTAS_PER_SEQ=g):
+    # G = 1; G = 3 as one thread-block cluster (DSMEM reduce); G = 3 and 29 on the global-memory barrier (cooperative launch)
+    for g, no_cluster in ((1, 0), (3, 0), (3, 1), (29, 1)):
+        with env(ODO_LM_CTAS_PER_SEQ=g, ODO_GROUP_NO_CLUSTER=no_cluster if no_cluster else ""):
+            if not no_cluster:
+                os.environ.pop("ODO_GROUP_NO_CLUSTER", None)
             rc, T, s2 = ctx.lm_solve(p1, d1, p2, capi.default_lm_params())
             l2 = ctx.lm_linearize(p1, d1, p2, 0, np.eye(4, dtype=np.float32))
-        assert rc == 0 and list(s2.iters) == list(base[2].iters)
+        assert rc == 0 and list(s2.iters) == list(base[2].iters), (g, no_cluster)
         assert np.abs(T - base[1]).max() < 1e-6
         assert l2["N"] == lin["N"] and np.abs(l2["H"] - lin["H"]).max() <= 1e-12 * np.abs(lin["H"]).max()
 
