@@ -54,9 +54,8 @@ def test_lm_group_sizes_agree(ctx, pair):
     assert base[0] == 0
     # G = 1; G = 3 as one thread-block cluster (DSMEM reduce); G = 3 and 29 on the global-memory barrier (cooperative launch)
     for g, no_cluster in ((1, 0), (3, 0), (3, 1), (29, 1)):
-        with env(ODO_LM_CTAS_PER_SEQ=g, ODO_GROUP_NO_CLUSTER=no_cluster if no_cluster else ""):
-            if not no_cluster:
-                os.environ.pop("ODO_GROUP_NO_CLUSTER", None)
+        kw = dict(ODO_LM_CTAS_PER_SEQ=g, **({"ODO_GROUP_NO_CLUSTER": 1} if no_cluster else {}))
+        with env(**kw):
             rc, T, s2 = ctx.lm_solve(p1, d1, p2, capi.default_lm_params())
             l2 = ctx.lm_linearize(p1, d1, p2, 0, np.eye(4, dtype=np.float32))
         assert rc == 0 and list(s2.iters) == list(base[2].iters), (g, no_cluster)
