@@ -12,6 +12,8 @@
 // L1/L2 (each input line is fetched from HBM once), batch index on blockIdx.z.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -107,6 +109,84 @@ __global__ void __launch_bounds__(128, 8) k_blur3(const SRC* __restrict__ src, i
       const float v = tap121(t0, t1, t2);
       *d = v;
       if (QOUT) bad |= !quant_store(qd, v);
+    }
+  }
+  if (QOUT && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&q.exact[blockIdx.z], 0);
+}
+
+// u8 frames: the same blur with the source tile staged in shared memory.  A CTA covers 128 columns x kBlurRows rows; the
+// kBlurRows + 2 source rows it needs are fetched with aligned 16-byte loads (an image row of 1241 bytes starts at any
+// alignment: each staged row keeps its own offset), after which the three taps of a pixel are shared-memory byte reads.
+// The byte-gather version above issues three global byte loads per pixel and row and sat at 1.6 TB/s; the arithmetic
+// (and so every output bit) is unchanged.  TMA is not an option for these inputs: cp.async.bulk / tensor maps need
+// 16-byte aligned rows, and the reference's frames are tightly packed with an odd width.
+constexpr int kBlurTileW = 128;
+constexpr int kBlurRowBytes = kBlurTileW + 2 + 30;   // tile + halo + alignment slack, rounded to 16: 160
+
+template <bool QOUT>
+__global__ void __launch_bounds__(128, 8) k_blur3_u8(const uint8_t* __restrict__ src, int64_t sstride, float* __restrict__ dst,
+                                                    int64_t dstride, int w, int h, QuantOut q) {
+  __shared__ __align__(16) uint8_t s_t[kBlurRows + 2][kBlurRowBytes];
+  __shared__ int s_off[kBlurRows + 2];   // smem index of image column c0 in each staged row
+  const int x0 = blockIdx.x * kBlurTileW, y0 = blockIdx.y * kBlurRows;
+  const uint8_t* s = src + (int64_t)blockIdx.z * sstride;
+  const int64_t img_bytes = (int64_t)w * h;
+  const int c0 = max(x0 - 1, 0), c1 = min(x0 + kBlurTileW, w - 1);   // staged image columns [c0, c1]
+  const int ncols = c1 - c0 + 1;
+  const int nrows = min(kBlurRows, h - y0) + 2;
+  // ---- stage: row slot r holds image row reflect101(y0 - 1 + r) ----
+  // alignment is taken on the ABSOLUTE address (the images of a batch follow each other at w*h bytes, any alignment);
+  // a vector that would reach in front of the batch or behind this image's last byte is assembled from byte loads
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(src), hi = reinterpret_cast<uintptr_t>(s) + (uintptr_t)img_bytes;
+  for (int i = threadIdx.x; i < nrows * 10; i += 128) {
+    const int r = i / 10, v = i - r * 10;
+    const int yy = reflect101(y0 - 1 + r, h);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s) + (uintptr_t)((int64_t)yy * w + c0);   // first byte wanted
+    const uintptr_t a_al = a & ~(uintptr_t)15;
+    if (v == 0) s_off[r] = (int)(a - a_al);
+    const uintptr_t g = a_al + 16u * (unsigned)v;      // this thread's 16 bytes
+    if (g < a + (uintptr_t)ncols) {
+      uint4 val;
+      if (g >= lo && g + 16 <= hi) {
+        val = __ldg(reinterpret_cast<const uint4*>(g));
+      } else {
+        uint8_t b[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) b[k] = (g + k >= lo && g + k < hi) ? __ldg(reinterpret_cast<const uint8_t*>(g + k)) : (uint8_t)0;
+        val.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24);
+        val.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((unsigned)b[7] << 24);
+        val.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((unsigned)b[11] << 24);
+        val.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((unsigned)b[15] << 24);
+      }
+      *reinterpret_cast<uint4*>(&s_t[r][16 * v]) = val;
+    }
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  bool bad = false;
+  if (x < w) {
+    // smem column indices of x - 1, x, x + 1 (reflected at the image border), relative to c0
+    const int im = reflect101(x - 1, w) - c0, ic = x - c0, ip = reflect101(x + 1, w) - c0;
+    float* d = dst + (int64_t)blockIdx.z * dstride + (int64_t)y0 * w + x;
+    uint16_t* qd = QOUT ? q.plane + (int64_t)blockIdx.z * q.stride + (int64_t)y0 * q.pitch + x : nullptr;
+    auto hrow = [&](int r) {
+      const uint8_t* p = &s_t[r][s_off[r]];
+      return tap121((float)p[im], (float)p[ic], (float)p[ip]);
+    };
+    float t0 = hrow(0), t1 = hrow(1);
+    const int nout = nrows - 2;
+#pragma unroll 16
+    for (int r = 0; r < nout; r++) {
+      const float t2 = hrow(r + 2);
+      const float v = tap121(t0, t1, t2);
+      *d = v;
+      d += w;
+      if (QOUT) {
+        bad |= !quant_store(qd, v);
+        qd += q.pitch;
+      }
+      t0 = t1;
+      t1 = t2;
     }
   }
   if (QOUT && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAnd(&q.exact[blockIdx.z], 0);
@@ -258,8 +338,14 @@ void launch_blur3(odo_ctx* c, ImgSrc src, int64_t sstride, float* dst, int64_t d
   dim3 grid((w + 127) / 128, (h + kBlurRows - 1) / kBlurRows, batch);
   if (src.u8) {
     const uint8_t* s8 = static_cast<const uint8_t*>(src.p);
-    if (q.plane) k_blur3<true, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
-    else k_blur3<false, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+    if (w >= 3 && h >= 2 && !std::getenv("ODO_BLUR_GATHER")) {   // shared-memory staged tile (default)
+      if (q.plane) k_blur3_u8<true><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+      else k_blur3_u8<false><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+    } else if (q.plane) {
+      k_blur3<true, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+    } else {
+      k_blur3<false, uint8_t><<<grid, 128, 0, c->stream>>>(s8, sstride, dst, dstride, w, h, q);
+    }
   } else {
     const float* sf = static_cast<const float*>(src.p);
     if (q.plane) k_blur3<true, float><<<grid, 128, 0, c->stream>>>(sf, sstride, dst, dstride, w, h, q);
