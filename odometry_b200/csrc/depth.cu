@@ -971,6 +971,8 @@ struct RefPass {
   const uint8_t* __restrict__ R8;
   float* dep;
   const int* __restrict__ sel_xy;
+  const int* boff;             // SHARED memory: exclusive prefix of the per-block selection counts ([512 + 1]); slot c of the
+                               // COMPACT list is entry c - boff[blk] of block blk's 80-entry list (holes are never visited)
   float2* __restrict__ st_a;   // {current, tmp}
   float2* jb;                  // SHARED memory: {jtwj, b} of this thread's slots, [trip][thread] -- written at the end of a
                                // visit and read at the start of the next one by the same thread, so it never has to leave the SM
@@ -981,6 +983,16 @@ struct RefPass {
   float txfx, gscale, wmax, huber_delta;
   bool use8;
 };
+
+// compact slot index -> index into the [512 blocks][80] selection list
+__device__ __forceinline__ int sel_slot(const int* boff, int c) {
+  int lo = 0, hi = kGridBlocks;   // boff[lo] <= c < boff[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (boff[mid] <= c) lo = mid; else hi = mid;
+  }
+  return lo * kSelMax + (c - boff[lo]);
+}
 
 template <bool FIRST>
 __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool accepted_once, float lambda,
@@ -1000,7 +1012,7 @@ __device__ __forceinline__ void refine_pass(const RefPass& rp, int pending, bool
       sb[u] = make_int2(-1, 0);
       if (s < rp.nslots) {
         if (FIRST) {
-          sb[u].x = rp.sel_xy[s];
+          sb[u].x = rp.sel_xy[sel_slot(rp.boff, s)];
         } else {
           sb[u] = rp.st_b[s];
           const float2 ct = rp.st_a[s];
@@ -1106,13 +1118,42 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   rp.R8 = d.rawR8 ? d.rawR8 + b * d.rawR8_stride : nullptr;
   rp.dep = dep;
   // pixel list (y << 16 | x), entries < 0 are holes; block-major selection order in the pipeline
-  rp.nslots = d.cap;
-  rp.sel_xy = d.sel_xy + (int64_t)b * rp.nslots;
-  rp.st_a = reinterpret_cast<float2*>(d.ref_state) + (int64_t)b * rp.nslots;
-  rp.st_b = reinterpret_cast<int2*>(d.ref_state + (int64_t)gridDim.y * 2 * rp.nslots) + (int64_t)b * rp.nslots;
+  // The selection lists are [512 blocks][80] with holes behind each block's last entry (a third of the slots on the
+  // street scene).  Lanes on holes idle while their warp works, so the passes walk a COMPACT index instead: an exclusive
+  // prefix of the per-block counts (shared memory, once per launch) maps it back to the list in the first pass.
+  __shared__ int s_boff[kGridBlocks + 1];
+  __shared__ int s_ws[kRefThreads / 32];
+  {
+    static_assert(kGridBlocks == 2 * kRefThreads, "two block counts per thread");
+    const int* cntp = d.sel_count + (int64_t)b * kGridBlocks;
+    const int c0 = cntp[2 * threadIdx.x], c1 = cntp[2 * threadIdx.x + 1];
+    int inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_ws[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int k = 0; k < kRefThreads / 32; k++)
+      if (k < (int)(threadIdx.x >> 5)) woff += s_ws[k];
+    const int exc = woff + inc - (c0 + c1);
+    s_boff[2 * threadIdx.x] = exc;
+    s_boff[2 * threadIdx.x + 1] = exc + c0;
+    if (threadIdx.x == kRefThreads - 1) s_boff[kGridBlocks] = woff + inc;
+    __syncthreads();
+  }
+  const int cap = d.cap;
+  rp.nslots = min(s_boff[kGridBlocks], cap);   // compact count
+  rp.boff = s_boff;
+  rp.sel_xy = d.sel_xy + (int64_t)b * cap;
+  rp.st_a = reinterpret_cast<float2*>(d.ref_state) + (int64_t)b * cap;
+  rp.st_b = reinterpret_cast<int2*>(d.ref_state + (int64_t)gridDim.y * 2 * cap) + (int64_t)b * cap;
   rp.jb_shared = jb_in_smem != 0;
   rp.jb = rp.jb_shared ? s_jb
-                       : reinterpret_cast<float2*>(d.ref_state + (int64_t)gridDim.y * 4 * rp.nslots) + (int64_t)b * rp.nslots;
+                       : reinterpret_cast<float2*>(d.ref_state + (int64_t)gridDim.y * 4 * cap) + (int64_t)b * cap;
   rp.W = W;
   rp.tid = blockIdx.x * kRefThreads + threadIdx.x;
   rp.nthreads = G * kRefThreads;
@@ -1165,7 +1206,7 @@ __global__ void __launch_bounds__(kRefThreads, 3) k_refine(const float* __restri
   // filter looks at is the one of the LAST evaluated tmp_depth: re-evaluated here from the same inputs.
   double nv[1] = {0.0};
   for (int s = rp.tid; s < rp.nslots && !too_many; s += rp.nthreads) {
-    const int yx = first ? rp.sel_xy[s] : rp.st_b[s].x;
+    const int yx = first ? rp.sel_xy[sel_slot(rp.boff, s)] : rp.st_b[s].x;
     if (yx < 0) continue;
     const int y = yx >> 16, x = yx & 0xffff;
     const int o = y * W + x;

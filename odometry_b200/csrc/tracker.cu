@@ -844,6 +844,10 @@ int odo_depth_optimize(odo_ctx* c, const float* left, const float* right, int w,
   ODO_CUDA_OK(c, cudaMemcpyAsync(dw.dep, dep, npx * 4, cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemcpyAsync(dw.val, val, npx, cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemcpyAsync(dw.sel_xy, list.data(), sizeof(int) * dw.cap, cudaMemcpyHostToDevice, c->stream));
+  // the raster-ordered list fills the [512][80] layout block after block: the per-block counts the kernel compacts with
+  std::vector<int> counts(512);
+  for (int i = 0; i < 512; i++) counts[i] = std::max(0, std::min(80, n - 80 * i));
+  ODO_CUDA_OK(c, cudaMemcpyAsync(dw.sel_count, counts.data(), sizeof(int) * 512, cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaMemcpyAsync(dw.stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
   ODO_CUDA_OK(c, cudaStreamSynchronize(c->stream));  // list/hs are host temporaries
   launch_depth_refine(c, dl, dr, 0, w, h, *p, dw, 1);
