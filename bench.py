@@ -153,14 +153,34 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
 
+_REAL_STDOUT = None
+
+
+def stdout_to_stderr():
+    """Everything any library writes to stdout from here on (NCCL's INFO log when NCCL_DEBUG=INFO is in the environment:
+    it cannot be re-routed from inside the process, tools/nccl_dbg_test.py) lands on stderr; the one JSON line goes to the
+    ORIGINAL stdout through emit().  bench.py does not touch NCCL_DEBUG."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def init_dist(dev, world):
-    """NCCL only carries the barrier / max-over-ranks plumbing.  Its INFO log (communicator size, transports) goes to
-    stderr so that stdout stays the one JSON line and the driver can still check the rank count."""
+    """NCCL only carries the barrier / max-over-ranks plumbing around the timed region."""
     if world <= 1:
         return
     import torch.distributed as dist
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 
 
@@ -354,7 +374,7 @@ def run_reference(args, rank, world):
         "pose_error_vs_gt": pose_error_summary([r[1] for r in last], gt[n_frames - 1]),
         "keyframes_in_timed_region": int(sum(n_kf)),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -449,7 +469,7 @@ def run_reference_4k(args, rank):
                              "sample": f"{n_seq} sequences x 1 frame (keyframe pyramids + frame pyramid + Solve), one per host thread; "
                                        + CPU_KIND_NOTE[kind]},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_4k(args, rank, local_rank, world):
@@ -463,7 +483,7 @@ def run_4k(args, rank, local_rank, world):
     init_dist(dev, world)
     line = measure_4k(args, rank, local_rank, world, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -672,7 +692,7 @@ def run_reference_rectify(args, rank):
                                        "(the reference calls OpenCV here; oracle/camera.cpp is pinned bit-exactly to cv2 4.13.0); "
                                        "host: " + host_cpu()},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_rectify(args, rank, local_rank, world):
@@ -772,7 +792,7 @@ def run_rectify(args, rank, local_rank, world):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": config_rect(args, B), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "pairs_per_step": world * B}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for c in cams:
         c.close()
     ctx.close()
@@ -782,6 +802,7 @@ def run_rectify(args, rank, local_rank, world):
 
 def main():
     args = parse()
+    stdout_to_stderr()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1090,7 +1111,7 @@ def run_kitti(args, rank, local_rank, world):
             line.update(latency)
         if cfg5:
             line["config5_4k"] = cfg5
-        print(json.dumps(line), flush=True)
+        emit(line)
     for c in ctxs:
         c.close()
     if world > 1:

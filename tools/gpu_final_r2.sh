@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 final GPU visit: parity tests, smoke, bench lines (default, S=1, 4K, rectify, reference arms), ncu launch list
 # with DRAM bytes and a --set full capture of three steady-state steps.
-TAG=${1:-r2k}
+TAG=${1:-r2q}
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi_$TAG.txt 2>&1
