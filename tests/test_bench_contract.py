@@ -54,3 +54,36 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                        text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_bench_host_helpers():
+    """host logic of bench.py that needs no GPU: weak / strong sequence split, ground-truth poses, pose-error summary,
+    sysfs cpulist parsing of the NUMA placement step"""
+    import argparse
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+
+    a = argparse.Namespace(seqs=64, seqs_total=0)
+    assert bench.seqs_per_gpu(a, 8) == (64, "weak")
+    a.seqs_total = 64
+    assert bench.seqs_per_gpu(a, 8) == (8, "strong") and bench.seqs_per_gpu(a, 1) == (64, "strong")
+    with pytest.raises(SystemExit):
+        bench.seqs_per_gpu(argparse.Namespace(seqs=64, seqs_total=10), 4)
+    gt = bench.gt_relative_poses(6)
+    assert np.allclose(gt[0], np.eye(4)) and abs(gt[5][2, 3] - 4.0) < 1e-3        # 0.8 m per frame forward
+    est = np.stack([gt[5], gt[5]]).astype(np.float32)
+    est[1, 0, 3] += 0.3
+    s = bench.pose_error_summary(est, gt[5])
+    assert s["max"] == pytest.approx(0.3, abs=1e-6) and s["median"] == pytest.approx(0.15, abs=1e-6)
+    assert s["max_rel"] == pytest.approx(0.3 / s["path_length_m"], rel=1e-6)
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+
+
+def test_stdout_is_one_json_line_even_if_a_library_prints():
+    """bench.py points fd 1 at stderr and writes its JSON line to the original stdout: anything a library prints to stdout
+    (NCCL's INFO log) cannot break the one-line contract"""
+    code = ("import sys, os; sys.path.insert(0, %r); import bench; bench.stdout_to_stderr(); "
+            "os.write(1, b'NCCL INFO noise\\n'); print('more noise'); bench.emit({'ok': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout == '{"ok": 1}\n' and "NCCL INFO noise" in r.stderr and "more noise" in r.stderr
