@@ -140,3 +140,38 @@ def test_pipelined_ingest_equals_synchronous_steps(ctx, synth_data):
             assert np.array_equal(pa, want[k][1]) and np.array_equal(pk, want[k][2])
             assert np.array_equal(kf, want[k][3])
         t.close()
+
+
+@pytest.mark.parametrize("w,h", [(333, 181), (640, 480), (1283, 97)])
+def test_u8_front_end_on_ragged_sizes(ctx, w, h):
+    """The u8-native kernels (shared-memory staged blur with per-row alignment offsets, byte-source pyrDown, refinement on
+    u8 frames) against the CV_32F path on sizes whose rows start at every alignment: tile edges, widths that are not a
+    multiple of the 128-column tile, images shorter than a strip.  Host u8, device-resident u8 at an odd base address and
+    float ingest must return the same bits (poses, keyframe flags, status) frame after frame."""
+    import torch
+    rng = np.random.default_rng(w * 1000 + h)
+    # blocky random albedo (strong edges over a quiet median gradient: the block-median selection finds plenty), the right
+    # eye a 20-pixel shift of the left (19 m, inside the 0.1-30 m range), the camera panning two pixels per frame
+    cells = rng.integers(40, 216, size=(h // 6 + 2, (w + 64) // 6 + 2)).astype(np.float32)
+    big = np.kron(cells, np.ones((6, 6), np.float32))[:h, :w + 48]
+    big = np.clip(big + rng.normal(0, 2, big.shape), 0, 255).astype(np.uint8)
+    frames = [(np.ascontiguousarray(big[:, 20 + 2 * k:20 + 2 * k + w]), np.ascontiguousarray(big[:, 40 + 2 * k:40 + 2 * k + w]))
+              for k in range(3)]
+    a = capi.Tracker(ctx, w, h, 3, 1)
+    b = capi.Tracker(ctx, w, h, 3, 1)
+    c = capi.Tracker(ctx, w, h, 3, 1)
+    pad = torch.zeros(2 * w * h + 3, dtype=torch.uint8, device="cuda")     # device frames at an ODD base address
+    for L, R in frames:
+        ra = a.step([L.astype(np.float32)], [R.astype(np.float32)])
+        rb = b.step([L], [R])
+        dl, dr = pad[1:1 + w * h], pad[1 + w * h:1 + 2 * w * h]
+        dl.copy_(torch.from_numpy(L.reshape(-1)).cuda())
+        dr.copy_(torch.from_numpy(R.reshape(-1)).cuda())
+        rc_ = c.step_dev(dl.data_ptr(), dr.data_ptr(), u8=True)
+        assert ra[0] == 0 and (ra[4] == 0).all(), "the synthetic pair must pass ComputeDepth (the comparison would be trivial otherwise)"
+        for r in (rb, rc_):
+            assert r[0] == ra[0]
+            assert np.array_equal(r[1], ra[1], equal_nan=True) and np.array_equal(r[2], ra[2], equal_nan=True)
+            assert np.array_equal(r[3], ra[3]) and np.array_equal(r[4], ra[4])
+    for t in (a, b, c):
+        t.close()
