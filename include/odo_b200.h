@@ -221,7 +221,9 @@ int  odo_tracker_step_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, con
  * contiguous [n_seq][h][w] float32 block per eye. */
 int  odo_tracker_step_dev(odo_tracker* t, const float* left_dev, const float* right_dev,
                           float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
-/* same without waiting (pair with odo_tracker_collect); the device buffers must stay untouched until then */
+/* same without waiting (pair with odo_tracker_collect); the device buffers must be COMPLETE when the call is made (the
+ * frame's pyramid is built on a stream of its own, ahead of the work queued before it) and stay untouched until the
+ * frame has been collected */
 int  odo_tracker_enqueue_dev(odo_tracker* t, const float* left_dev, const float* right_dev);
 /* the same two for CV_8U frames resident on the device ([n_seq][h][w] bytes per eye), the format imread(GRAYSCALE)
  * produces (run_odometry_kitti_offline.cpp:342-347): the convertTo(CV_32F) of :348,358 happens on load inside the
@@ -230,8 +232,9 @@ int  odo_tracker_step_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint
                              float* pose_abs, float* pose_kf, int* is_keyframe, int* status);
 int  odo_tracker_enqueue_dev_u8(odo_tracker* t, const uint8_t* left_dev, const uint8_t* right_dev);
 
-/* device time of the stages of the last step, in ms (CUDA events on the context's stream):
- * 0 image pyramid, 1 LM solve + pose update, 2 blur + selection, 3 disparity search,
+/* device time of the stages of the last step, in ms (CUDA events on the stream each stage runs on):
+ * 0 image pyramid (built on its own stream while the previous frame is still in flight: a span, not a kernel time),
+ * 1 LM solve + pose update (own stream), 2 blur + selection, 3 disparity search,
  * 4 depth refinement, 5 depth pyramid + keyframe promotion + LM point lists */
 #define ODO_N_STAGES 6
 int  odo_tracker_stage_ms(const odo_tracker* t, float* ms_out /* [ODO_N_STAGES] */);

@@ -216,6 +216,7 @@ struct DepthWork {
 };
 size_t depth_work_bytes(int w, int h, int batch, bool debug);
 int depth_slots();  // capacity of the per-sequence pixel list (512 blocks x 80)
+int64_t depth_q_plane_elems(int w, int h);  // u16 elements of one sequence's q plane (an extra left plane per ingest slot)
 void depth_work_bind(DepthWork* d, void* mem, int w, int h, int batch, bool debug);
 // blur_left_done: d.blurL already holds GaussianBlur(L) (image pyramid level 0 of the same frame)
 QuantOut depth_quant_left(const DepthWork& d, const odo_depth_params& p, int w, int h);  // q output of the left blur

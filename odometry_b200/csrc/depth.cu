@@ -1274,6 +1274,8 @@ size_t depth_work_bytes(int w, int h, int batch, bool debug) {
   return bytes;
 }
 
+int64_t depth_q_plane_elems(int w, int h) { return (int64_t)q_pitch(w) * h + 16; }   // per sequence, u16 elements (+16: vector staging)
+
 int depth_slots() { return kGridBlocks * kSelMax; 
 }
 

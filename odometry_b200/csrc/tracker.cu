@@ -220,6 +220,16 @@ struct odo_tracker {
   int64_t n_enqueued = 0, n_collected = 0;
   bool lm_ran[2] = {false, false};
   float *cur_img = nullptr, *cur_dep = nullptr;
+  // The image pyramid (and the left q plane / exactness flags its level-0 blur emits) exists once per ingest slot: the
+  // pyramid of frame k+1 depends on nothing but its input, so it is built on `pre_stream` while frame k's solve is still
+  // running, and the LM chain of frame k+1 starts the moment frame k's pose and point lists are there.
+  float* img_slot[2] = {nullptr, nullptr};
+  uint16_t* qL_slot[2] = {nullptr, nullptr};
+  int* exact_slot[2] = {nullptr, nullptr};
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t ev_pyr[2] = {nullptr, nullptr};       // pre stream: the slot's pyramid is built
+  cudaEvent_t ev_img_free[2] = {nullptr, nullptr};  // compute stream: the last reader of the slot's pyramid is queued
+  cudaEvent_t ev_in_ready = nullptr;                // compute stream: device-side producer of the raw frames (remap) is queued
   DepthWork dw;
   LmLists lists;
   LmWork lmw;
@@ -251,7 +261,10 @@ struct StreamScope {
 // L, R: the raw frames of the batch, CV_32F or CV_8U (u8-native front end: every kernel that reads a raw frame converts
 // on load, nothing is converted ahead).  R8: the raw right frames as u8 when a float R comes with a u8 twin (raw-camera
 // ingest), else nullptr.
-static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const uint8_t* R8 = nullptr) {
+// in_ready: the event after which the raw frames are on the device (host paths: the slot's copy; raw-camera path: the remap;
+// device-resident frames: nullptr, they are complete before the call by contract).
+static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const uint8_t* R8 = nullptr,
+                          cudaEvent_t in_ready = nullptr) {
   if (R.u8) R8 = R.b8();
   odo_ctx* c = t->c;
   const int n = t->n;
@@ -259,25 +272,34 @@ static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const ui
   const int64_t in_stride = t->npx;
   cudaEvent_t* ev = t->ev[slot];
   c->err.clear();
-  cudaEventRecord(ev[0], c->stream);
-  // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130)
-  // level 0 doubles as the blurred left image of the depth stage: emit its u16 copy for the integer line search
-  depth_quant_reset(c, t->dw, n);
-  // level 0 here; levels 1.. are only read by the LM solve (and, after the join, by the point-list build): on frames
-  // that track they are built on the LM stream, off the critical path of the depth pipeline
-  launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, depth_quant_left(t->dw, t->dp, t->w, t->h),
-                       first ? PYR_ALL : PYR_LEVEL0);
-  cudaEventRecord(ev[1], c->stream);
+  // ImagePyramid cur(levels, left, true) (:205 ; frame 0: :130) on the pre stream: it waits for the frame's input and for
+  // the previous user of this slot's pyramid (two frames ago), NOT for the frame in front of it.  Level 0 doubles as the
+  // blurred left image of the depth stage: it also emits the u16 plane for the integer line search.
+  t->cur_img = t->img_slot[slot];
+  t->dw.blurL = t->cur_img;
+  t->dw.qL = t->qL_slot[slot];
+  t->dw.exact = t->exact_slot[slot];
+  if (in_ready) cudaStreamWaitEvent(t->pre_stream, in_ready, 0);
+  if (t->frame_id >= 2) cudaStreamWaitEvent(t->pre_stream, t->ev_img_free[slot], 0);
+  {
+    StreamScope on_pre(c, t->pre_stream);
+    cudaEventRecord(ev[0], t->pre_stream);
+    depth_quant_reset(c, t->dw, n);
+    launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, depth_quant_left(t->dw, t->dp, t->w, t->h), PYR_ALL);
+    cudaEventRecord(ev[1], t->pre_stream);
+    cudaEventRecord(t->ev_pyr[slot], t->pre_stream);
+  }
+  cudaStreamWaitEvent(c->stream, t->ev_pyr[slot], 0);
   t->lm_ran[slot] = !first;
   if (!first) {
-    // Solve against the keyframe (:215), forked onto the LM stream
+    // Solve against the keyframe (:215), forked onto the LM stream (the fork point is behind the previous frame's pose
+    // update and point-list build on the compute stream, and behind this frame's pyramid)
     cudaEventRecord(t->ev_fork, c->stream);
     cudaStreamWaitEvent(t->lm_stream, t->ev_fork, 0);
     int rc;
     {
       StreamScope on_lm(c, t->lm_stream);
       cudaEventRecord(t->ev_lm[slot][0], t->lm_stream);
-      launch_image_pyramid(c, L, in_stride, t->cur_img, t->pyr_stride, t->g, 1, n, QuantOut(), PYR_UPPER_LEVELS);
       rc = launch_lm_solve(c, t->lists, t->cur_img, t->pyr_stride, t->g, t->lm, t->T_init, t->res, t->lmw, n, t->G_lm, -1);
       if (rc == 0) {
         k_track_pose<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->res, t->T_init, n);
@@ -305,7 +327,7 @@ static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const ui
   // it through level 0, nothing else in the loop looks at levels 1.., so it is not materialised
   if (!first) {
     cudaStreamWaitEvent(c->stream, t->ev_lm_done, 0);  // join: the keyframe rule needs the pose
-    cudaEventRecord(t->ev_consumed[slot], c->stream);  // the LM stream read the raw frame too (pyramid level 1, quirk Q5)
+    cudaEventRecord(t->ev_consumed[slot], c->stream);  // (the pre stream's reads of the raw frame ended before selection began)
   }
   k_track_finalize<<<(n + 63) / 64, 64, 0, c->stream>>>(t->state, t->dw.stats, t->promote, first, n);
   c->launches++;
@@ -314,6 +336,7 @@ static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const ui
   launch_lm_prepare(c, t->cur_img, t->pyr_stride, t->cur_dep, t->pyr_stride, t->g, t->lm.K, t->lists, n, t->promote,
                     /*dep_from_l0=*/1);
   t->lm.lambda = 0.01f;  // Reset(pose, 0.01f)
+  cudaEventRecord(t->ev_img_free[slot], c->stream);  // solve, selection, line search and list build of this frame are queued
   cudaEventRecord(ev[6], c->stream);
   ODO_CUDA_OK(c, cudaMemcpyAsync(t->h_state[slot], t->state, sizeof(SeqState) * n, cudaMemcpyDeviceToHost, c->stream));
   ODO_CUDA_OK(c, cudaEventRecord(t->ev_done[slot], c->stream));
@@ -350,6 +373,7 @@ static int tracker_finish(odo_tracker* t, int slot, float* pose_abs, float* pose
 static int tracker_break(odo_tracker* t) {
   const std::string why = t->c->err;
   cudaStreamSynchronize(t->copy_stream);
+  cudaStreamSynchronize(t->pre_stream);
   cudaStreamSynchronize(t->lm_stream);
   cudaStreamSynchronize(t->c->stream);
   t->broken = true;
@@ -411,7 +435,7 @@ static int tracker_enqueue(odo_tracker* t, const T* const* left, const T* const*
   // run_odometry_kitti_offline.cpp:348,358, happens on load inside the blur / pyrDown / refinement kernels
   const ImgSrc Ls = u8 ? ImgSrc(t->in_u8[slot]) : ImgSrc(t->in_left[slot]);
   const ImgSrc Rs = u8 ? ImgSrc(t->in_u8[slot] + (size_t)t->n * t->npx) : ImgSrc(t->in_right[slot]);
-  if (tracker_launch(t, Ls, Rs, slot) != 0) return tracker_break(t);
+  if (tracker_launch(t, Ls, Rs, slot, nullptr, t->ev_copied[slot]) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
@@ -464,7 +488,9 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
   const size_t rs_b = al256(sizeof(LmResult) * n_seq);
   const size_t st_b = al256(sizeof(SeqState) * n_seq);
   const size_t pf_b = al256(sizeof(int) * n_seq);
-  bytes = (in_b * 2 + u8_b) * 2 + pyr_b * 2 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b;
+  const size_t ql_b = al256(sizeof(uint16_t) * (size_t)depth_q_plane_elems(w, h) * n_seq);
+  const size_t ex_b = al256(sizeof(int) * n_seq);
+  bytes = (in_b * 2 + u8_b) * 2 + pyr_b * 3 + dw_b + ll_b + lw_b + ti_b + rs_b + st_b + pf_b + ql_b + ex_b;
   if (cudaMalloc(&t->mem, bytes) != cudaSuccess) {
     c->err = "tracker: cudaMalloc failed";
     delete t;
@@ -477,9 +503,15 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
     t->in_right[k] = (float*)p; p += in_b;
     t->in_u8[k] = (uint8_t*)p; p += u8_b;
   }
-  t->cur_img = (float*)p; p += pyr_b;
+  t->img_slot[0] = (float*)p; p += pyr_b;
+  t->img_slot[1] = (float*)p; p += pyr_b;
+  t->cur_img = t->img_slot[0];
   t->cur_dep = (float*)p; p += pyr_b;
   depth_work_bind(&t->dw, p, w, h, n_seq, false); p += dw_b;
+  t->qL_slot[0] = t->dw.qL;                     // slot 0 uses the depth work area's own left q plane and flags
+  t->exact_slot[0] = t->dw.exact;
+  t->qL_slot[1] = (uint16_t*)p; p += ql_b;
+  t->exact_slot[1] = (int*)p; p += ex_b;
   // level 0 of the image pyramid IS GaussianBlur(left) and level 0 of the depth pyramid IS the refined
   // inverse depth: alias them instead of computing / copying them twice; the disparity map is a display
   // output of ComputeDepth that the tracking loop never reads
@@ -512,6 +544,12 @@ int odo_tracker_create(odo_ctx* c, int w, int h, int levels, int n_seq, const od
     const char* e = std::getenv("ODO_LM_STREAM_PRIORITY");
     const bool prio = !(e && e[0] == '0');
     ok(cudaStreamCreateWithPriority(&t->lm_stream, cudaStreamNonBlocking, prio ? hi : 0));
+  }
+  ok(cudaStreamCreateWithFlags(&t->pre_stream, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&t->ev_in_ready, cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) {
+    ok(cudaEventCreateWithFlags(&t->ev_pyr[k], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&t->ev_img_free[k], cudaEventDisableTiming));
   }
   ok(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&t->ev_lm_done, cudaEventDisableTiming));
@@ -549,6 +587,15 @@ void odo_tracker_destroy(odo_tracker* t) {
   if (t->lm_stream) {
     cudaStreamSynchronize(t->lm_stream);
     cudaStreamDestroy(t->lm_stream);
+  }
+  if (t->pre_stream) {
+    cudaStreamSynchronize(t->pre_stream);
+    cudaStreamDestroy(t->pre_stream);
+  }
+  if (t->ev_in_ready) cudaEventDestroy(t->ev_in_ready);
+  for (int k = 0; k < 2; k++) {
+    if (t->ev_pyr[k]) cudaEventDestroy(t->ev_pyr[k]);
+    if (t->ev_img_free[k]) cudaEventDestroy(t->ev_img_free[k]);
   }
   if (t->ev_fork) cudaEventDestroy(t->ev_fork);
   if (t->ev_lm_done) cudaEventDestroy(t->ev_lm_done);
@@ -684,7 +731,8 @@ int odo_tracker_enqueue_raw_u8(odo_tracker* t, const uint8_t* const* left_raw, c
     c->err = "tracker: remap launch failed";
     return -1;
   }
-  if (tracker_launch(t, ImgSrc(t->in_left[slot]), ImgSrc(t->in_right[slot]), slot, R8) != 0) return tracker_break(t);
+  ODO_CUDA_OK(c, cudaEventRecord(t->ev_in_ready, c->stream));   // the remap that produces the frames is queued on the compute stream
+  if (tracker_launch(t, ImgSrc(t->in_left[slot]), ImgSrc(t->in_right[slot]), slot, R8, t->ev_in_ready) != 0) return tracker_break(t);
   t->n_enqueued++;
   return 0;
 }
