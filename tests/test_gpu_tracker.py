@@ -73,6 +73,7 @@ def test_device_resident_u8_frames_equal_float_ingest(ctx, synth_data):
         ra = a.step([s["frames"][k][0].astype(np.float32) for s in seqs], [s["frames"][k][1].astype(np.float32) for s in seqs])
         L = torch.from_numpy(np.stack([s["frames"][k][0] for s in seqs])).cuda()
         R = torch.from_numpy(np.stack([s["frames"][k][1] for s in seqs])).cuda()
+        torch.cuda.synchronize()
         rb = b.step_dev(L.data_ptr(), R.data_ptr(), u8=True)
         assert ra[0] == rb[0] == 0
         assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
@@ -167,6 +168,7 @@ def test_u8_front_end_on_ragged_sizes(ctx, w, h):
         dl, dr = pad[1:1 + w * h], pad[1 + w * h:1 + 2 * w * h]
         dl.copy_(torch.from_numpy(L.reshape(-1)).cuda())
         dr.copy_(torch.from_numpy(R.reshape(-1)).cuda())
+        torch.cuda.synchronize()     # device-resident frames must be complete when the call is made (include/odo_b200.h)
         rc_ = c.step_dev(dl.data_ptr(), dr.data_ptr(), u8=True)
         assert ra[0] == 0 and (ra[4] == 0).all(), "the synthetic pair must pass ComputeDepth (the comparison would be trivial otherwise)"
         for r in (rb, rc_):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 final GPU visit: parity tests, smoke, bench lines (default, S=1, 4K, rectify, reference arms), ncu launch list
 # with DRAM bytes and a --set full capture of three steady-state steps.
-TAG=${1:-r2q}
+TAG=${1:-r2s}
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi_$TAG.txt 2>&1
@@ -14,9 +14,9 @@ timeout 300 python bench.py --seqs 1 --steps 50 --no-cpu-baseline --no-extras > 
 for S in 8 16 32; do timeout 300 python bench.py --seqs $S --steps 40 --no-cpu-baseline --no-extras > $O/bench_${TAG}_s$S.json 2> $O/bench_${TAG}_s$S.err; done
 timeout 600 python bench.py --workload 4k --steps 10 > $O/bench_${TAG}_4k.json 2> $O/bench_${TAG}_4k.err
 timeout 300 python bench.py --workload rectify > $O/bench_${TAG}_rectify.json 2> $O/bench_${TAG}_rectify.err
-timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_" -c 300 --csv --log-file $O/launches_$TAG.csv \
+[ -n "$NO_NCU" ] || timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_" -c 300 --csv --log-file $O/launches_$TAG.csv \
   python bench.py --seqs 64 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > $O/ncu_launches_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:"k_" -s 78 -c 19 -o $O/full_$TAG -f \
+[ -n "$NO_NCU" ] || timeout 900 ncu --set full --clock-control none -k regex:"k_" -s 78 -c 19 -o $O/full_$TAG -f \
   python bench.py --seqs 64 --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > $O/ncu_full_$TAG.log 2>&1
 python - <<PY
 import json

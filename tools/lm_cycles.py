@@ -9,6 +9,7 @@ fr = bench.render_sequences(list(range(S)), 6, "cuda").to(torch.float32)
 ctx = capi.Context(0)
 trk = capi.Tracker(ctx, 1241, 376, 4, S)
 L = fr[:, :, 0].contiguous(); R = fr[:, :, 1].contiguous()
+torch.cuda.synchronize()   # device-resident frames must be complete before odo_tracker_step_dev
 for f in range(6):
     trk.step_dev(L[f].data_ptr(), R[f].data_ptr())
     if f:
