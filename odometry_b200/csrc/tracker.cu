@@ -292,10 +292,12 @@ static int tracker_launch(odo_tracker* t, ImgSrc L, ImgSrc R, int slot, const ui
   cudaStreamWaitEvent(c->stream, t->ev_pyr[slot], 0);
   t->lm_ran[slot] = !first;
   if (!first) {
-    // Solve against the keyframe (:215), forked onto the LM stream (the fork point is behind the previous frame's pose
-    // update and point-list build on the compute stream, and behind this frame's pyramid)
-    cudaEventRecord(t->ev_fork, c->stream);
-    cudaStreamWaitEvent(t->lm_stream, t->ev_fork, 0);
+    // Solve against the keyframe (:215) on the LM stream.  It waits for exactly what it needs: this frame's pyramid (pre
+    // stream) and the END of the previous frame on the compute stream (ev_done of the other slot: point lists built, and
+    // the per-sequence state copied out -- this frame's pose update overwrites it); the previous pose update itself is
+    // on the LM stream.
+    cudaStreamWaitEvent(t->lm_stream, t->ev_pyr[slot], 0);
+    cudaStreamWaitEvent(t->lm_stream, t->ev_done[slot ^ 1], 0);
     int rc;
     {
       StreamScope on_lm(c, t->lm_stream);
