@@ -11,7 +11,9 @@ attacked on the CPU with random and adversarial operands.
   * div_by_f, f_over_z (lm.cu): the fp64 quotients of ReprojectToCameraFrame / the warp Jacobian
     (include/image_processing_global.h:31-39, src/lm_optimizer.cpp:223-233) through one reciprocal;
   * the squared-magnitude threshold of k_select_tile (depth.cu): `sqrt(v) > th` (src/depth_estimate.cpp:330) as
-    `v >= tv`.
+    `v >= tv`;
+  * the integer cost of k_disparity (depth.cu) against the fp32 hadd tree of ComputeSsdPattern8Sse
+    (src/depth_estimate.cpp:435-453).
 """
 from fractions import Fraction
 
@@ -239,3 +241,31 @@ def test_squared_threshold_selects_exactly_the_pixels_above_the_threshold(seed):
     v = g[:, 0] * g[:, 0] + g[:, 1] * g[:, 1]
     t = th[:n]
     assert np.array_equal(np.sqrt(v) > t, v >= squared_threshold(t))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# integer SSD of the line search
+# ------------------------------------------------------------------------------------------------------------------
+def ssd_tree_f32(l, r):
+    """ComputeSsdPattern8Sse (src/depth_estimate.cpp:435-453): fp32 differences, squares and the hadd tree"""
+    s = (l - r) * (l - r)
+    return ((s[..., 0] + s[..., 1]) + (s[..., 2] + s[..., 3])) + ((s[..., 4] + s[..., 5]) + (s[..., 6] + s[..., 7]))
+
+
+@pytest.mark.parametrize("spread", [40, 600, 4080])
+def test_integer_ssd_equals_the_fp32_tree_wherever_a_match_is_possible(spread):
+    """k_disparity's integer path: blurred u8-sourced pixels are multiples of 1/16, q = 16 * blur, and 256 * SSD is the
+    integer sum of (ql - qr)^2.  Below 2^24 (SSD < 65536, far above any usable ssd_th) every partial sum of the fp32 tree
+    is exact, so the float cost IS the integer cost / 256 and `first minimum` / `<= ssd_th` decide identically; above it
+    the float cost stays above 65535, i.e. such a candidate can neither win against an exact one nor pass the threshold."""
+    rng = np.random.default_rng(spread)
+    n = 1_000_000
+    ql = rng.integers(0, 4081, (n, 8))
+    qr = np.clip(ql + rng.integers(-spread, spread + 1, (n, 8)), 0, 4080)
+    cost = ((ql - qr) ** 2).sum(axis=1)
+    f = ssd_tree_f32(ql.astype(F32) / F32(16), qr.astype(F32) / F32(16))
+    small = cost < (1 << 24)
+    assert np.array_equal(f[small].astype(np.float64) * 256.0, cost[small].astype(np.float64))
+    assert (f[~small] > 65535.0).all()
+    if spread == 4080:
+        assert (~small).any() and small.any()
